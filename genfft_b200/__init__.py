@@ -1,0 +1,10 @@
+"""genfft_b200 -- B200-native FFT engine behind genFFT's API.
+
+The package is a thin host layer over ``lib/libgenfft_cuda.so`` (hand-written sm_100a CUDA behind the C ABI
+of ``include/genfft_cuda.h``).  It has no CPU or PyTorch compute path.
+"""
+from ._lib import F32, F64, GenfftCudaError, LIB_PATH, build, exported_symbols, lib
+from .api import DIT, FFT, FFT2D, FFTVert, RealFFT, device_count, launch_count
+
+__all__ = ["FFT", "FFTVert", "DIT", "FFT2D", "RealFFT", "F32", "F64", "GenfftCudaError", "LIB_PATH", "build",
+           "exported_symbols", "lib", "device_count", "launch_count"]

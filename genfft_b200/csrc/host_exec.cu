@@ -1,0 +1,209 @@
+// libgenfft_cuda: host-pointer entry points -- the literal drop-in for the reference's CPU callers
+// (FFT<T>::transform(std::complex<T>* out, const std::complex<T>* in), include/genFFT/fft.h:80-85, etc.).
+// The library stages host<->device copies itself.  Batched 1D plans that need no scratch are cut into
+// chunks that alternate between two streams, so chunk i's D2H, chunk i+1's kernels and chunk i+2's H2D
+// overlap (PCIe is full duplex and the copy engines are independent of the SMs).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "../../include/genfft_cuda.h"
+#include "plan.h"
+
+using namespace genfft_cuda;
+
+
+#define HX_TRY(expr)                                                        \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) {                                                \
+      std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);  \
+      return set_error(GENFFT_CUDA_ERR_CUDA, m.c_str());                    \
+    }                                                                       \
+  } while (0)
+
+static int ensure_stage(Plan* p, size_t in_bytes, size_t out_bytes) {
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (p->stage_in_bytes < in_bytes) {
+    if (p->stage_in) cudaFree(p->stage_in);
+    p->stage_in = nullptr;
+    p->stage_in_bytes = 0;
+    if (cudaMalloc(&p->stage_in, in_bytes) != cudaSuccess) return set_error(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc of input staging failed");
+    p->stage_in_bytes = in_bytes;
+  }
+  if (p->stage_out_bytes < out_bytes) {
+    if (p->stage_out) cudaFree(p->stage_out);
+    p->stage_out = nullptr;
+    p->stage_out_bytes = 0;
+    if (cudaMalloc(&p->stage_out, out_bytes) != cudaSuccess) return set_error(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc of output staging failed");
+    p->stage_out_bytes = out_bytes;
+  }
+  if (!p->streams_ready) {
+    for (auto& s : p->streams) HX_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    p->streams_ready = true;
+  }
+  return GENFFT_CUDA_OK;
+}
+
+static size_t chunk_bytes_target() {
+  const char* s = getenv("GENFFT_CUDA_HOST_CHUNK_MB");
+  size_t mb = s && *s ? (size_t)atol(s) : 64;
+  return std::max<size_t>(mb, 1) << 20;
+}
+
+// batched 1D (c2c or r2c): in/out element sizes and distances differ between the two
+static int exec_batched_host(Plan* p, void* out, const void* in, size_t in_elem, long long in_dist, long long in_len,
+                             size_t out_elem, long long out_dist, long long out_len, bool r2c, int inverse,
+                             bool brev, bool real_in) {
+  const long long batch = p->batch;
+  const size_t in_row = (size_t)in_dist * in_elem, out_row = (size_t)out_dist * out_elem;
+  const size_t in_last = (size_t)in_len * in_elem, out_last = (size_t)out_len * out_elem;
+  const bool pipelined = batch > 1 && !plan_needs_scratch(p) && !brev;
+  long long chunk = batch;
+  int nbuf = 1;
+  if (pipelined) {
+    chunk = std::max<long long>(1, (long long)(chunk_bytes_target() / std::max(in_row, out_row)));
+    chunk = std::min(chunk, batch);
+    if (chunk < batch) nbuf = 2;
+  }
+  const size_t in_chunk = (size_t)(chunk - 1) * in_row + in_last, out_chunk = (size_t)(chunk - 1) * out_row + out_last;
+  // 256-byte aligned sub-buffers
+  const size_t in_slot = (in_chunk + 255) & ~(size_t)255, out_slot = (out_chunk + 255) & ~(size_t)255;
+  int rc = ensure_stage(p, in_slot * nbuf, out_slot * nbuf);
+  if (rc) return rc;
+  int slot = 0;
+  for (long long b0 = 0; b0 < batch; b0 += chunk, slot ^= (nbuf - 1)) {
+    const long long nb = std::min(chunk, batch - b0);
+    cudaStream_t st = p->streams[slot];
+    char* din = (char*)p->stage_in + slot * in_slot;
+    char* dout = (char*)p->stage_out + slot * out_slot;
+    const size_t ib = (size_t)(nb - 1) * in_row + in_last, ob = (size_t)(nb - 1) * out_row + out_last;
+    HX_TRY(cudaMemcpyAsync(din, (const char*)in + (size_t)b0 * in_row, ib, cudaMemcpyHostToDevice, st));
+    rc = r2c ? exec_r2c_internal(p, dout, din, st, nb)
+             : exec_c2c_internal(p, brev ? din : dout, din, inverse, st, brev, real_in, nb);
+    if (rc) return rc;
+    HX_TRY(cudaMemcpyAsync((char*)out + (size_t)b0 * out_row, brev ? din : dout, ob, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < nbuf; s++) HX_TRY(cudaStreamSynchronize(p->streams[s]));
+  return GENFFT_CUDA_OK;
+}
+
+extern "C" {
+
+int genfft_cuda_exec_c2c(genfft_cuda_plan_t plan, void* out, const void* in, int inverse) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in) return set_error(GENFFT_CUDA_ERR_ARG, "FFT::transform requires out != in");
+  const size_t es = elem_size(p->precision);
+  return exec_batched_host(p, out, in, es, p->in_dist, p->n, es, p->out_dist, p->n, false, inverse, false, false);
+}
+
+int genfft_cuda_exec_c2c_no_scramble(genfft_cuda_plan_t plan, void* inout, int inverse) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (!inout) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (p->in_dist != p->out_dist) return set_error(GENFFT_CUDA_ERR_ARG, "in-place transform needs in_dist == out_dist");
+  const size_t es = elem_size(p->precision);
+  return exec_batched_host(p, inout, inout, es, p->in_dist, p->n, es, p->out_dist, p->n, false, inverse, true, false);
+}
+
+int genfft_cuda_exec_c2c_real_in(genfft_cuda_plan_t plan, void* out, const void* in_real) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (!out || !in_real) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  const size_t es = elem_size(p->precision);
+  return exec_batched_host(p, out, in_real, es / 2, p->in_dist, p->n, es, p->out_dist, p->n, false, 0, false, true);
+}
+
+int genfft_cuda_exec_r2c(genfft_cuda_plan_t plan, void* out, const void* in) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_R2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_1d plan");
+  if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  const size_t es = elem_size(p->precision);
+  const long long out_len = p->n == 1 ? 1 : (p->half ? p->n / 2 + 1 : p->n);
+  return exec_batched_host(p, out, in, es / 2, p->in_dist, p->n, es, p->out_dist, out_len, true, 0, false, false);
+}
+
+int genfft_cuda_exec_c2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in, int64_t in_stride,
+                            int inverse) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2C_2D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_2d plan");
+  if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in) return set_error(GENFFT_CUDA_ERR_ARG, "FFT2D::transform requires out != in");
+  if (out_stride < p->width || in_stride < p->width) return set_error(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
+  const size_t es = elem_size(p->precision);
+  const size_t dense = (size_t)p->width * p->height * es;
+  int rc = ensure_stage(p, dense, dense);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  HX_TRY(cudaMemcpy2DAsync(p->stage_in, p->width * es, in, in_stride * es, p->width * es, p->height, cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_c2c_2d_dev(plan, p->stage_out, p->width, p->stage_in, p->width, inverse, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpy2DAsync(out, out_stride * es, p->stage_out, p->width * es, p->width * es, p->height, cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_exec_vert(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in, int64_t in_stride,
+                          int64_t cols, int inverse) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_VERT) return set_error(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in) return set_error(GENFFT_CUDA_ERR_ARG, "FFTVert::transform requires out != in");
+  if (cols < 0 || out_stride < cols || in_stride < cols) return set_error(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
+  if (cols == 0) return GENFFT_CUDA_OK;
+  const size_t es = elem_size(p->precision);
+  const size_t dense = (size_t)cols * p->n * es;
+  int rc = ensure_stage(p, dense, dense);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  HX_TRY(cudaMemcpy2DAsync(p->stage_in, cols * es, in, in_stride * es, cols * es, p->n, cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_vert_dev(plan, p->stage_out, cols, p->stage_in, cols, cols, inverse, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpy2DAsync(out, out_stride * es, p->stage_out, cols * es, cols * es, p->n, cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_exec_vert_no_scramble(genfft_cuda_plan_t plan, void* data, int64_t stride, int64_t cols, int inverse) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_VERT) return set_error(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  if (!data) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (cols < 0 || stride < cols) return set_error(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
+  if (cols == 0) return GENFFT_CUDA_OK;
+  const size_t es = elem_size(p->precision);
+  const size_t dense = (size_t)cols * p->n * es;
+  int rc = ensure_stage(p, dense, 256);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  HX_TRY(cudaMemcpy2DAsync(p->stage_in, cols * es, data, stride * es, cols * es, p->n, cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_vert_no_scramble_dev(plan, p->stage_in, cols, cols, inverse, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpy2DAsync(data, stride * es, p->stage_in, cols * es, cols * es, p->n, cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_exec_dit(genfft_cuda_plan_t plan, void* out, const void* in, int half) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_DIT) return set_error(GENFFT_CUDA_ERR_ARG, "not a dit plan");
+  if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  const size_t es = elem_size(p->precision);
+  const long long n = p->n;
+  const size_t in_bytes = (size_t)std::max<long long>(1, n / 2) * es;
+  const size_t out_bytes = (size_t)(n <= 1 ? 1 : (half ? n / 2 + 1 : n)) * es;
+  // the split runs in place on the device copy of the input (as RealFFT::forward does, FFTReal.h:211)
+  int rc = ensure_stage(p, std::max(in_bytes, out_bytes), 256);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  HX_TRY(cudaMemcpyAsync(p->stage_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_dit_dev(plan, p->stage_in, p->stage_in, half, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpyAsync(out, p->stage_in, out_bytes, cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1065 @@
+// libgenfft_cuda: plans, pass emission and execution (host side).
+//
+// The reference builds an "impl" per size from a factory switch (include/genFFT/x86/fft_float_impl_x86.inl:464-497)
+// whose constructor chain computes one twiddle table per radix-2 level (include/genFFT/FFTTwiddle.h:44-51).
+// Here a plan is a short list of Stockham passes (1 for sizes that fit on chip, 2-3 above), each a
+// launch of the tile kernel with its own addressing, plus fp64-computed twiddle tables stored at the
+// transform's precision.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/genfft_cuda.h"
+#include "aux_kernels.cuh"
+#include "plan.h"
+
+namespace genfft_cuda {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(GENFFT_CUDA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                  __FILE__, __LINE__);                                                            \
+  } while (0)
+
+size_t elem_size(int precision) { return precision == GENFFT_CUDA_F32 ? 8 : 16; }
+
+static bool is_pow2(long long n) { return n >= 1 && (n & (n - 1)) == 0; }
+static int ilog2(long long n) {
+  int l = 0;
+  while ((1LL << l) < n) l++;
+  return l;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------------
+static int usable_device(int* dev_out, int* sms_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(GENFFT_CUDA_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  int major = 0, sms = 0;
+  CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10)
+    return fail(GENFFT_CUDA_ERR_CUDA, "device %d has compute capability %d.x; this library is built for sm_100a only",
+                dev, major);
+  *dev_out = dev;
+  *sms_out = sms;
+  return GENFFT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel registry
+// ------------------------------------------------------------------------------------------------
+static std::vector<KernelEntry>& registry(int precision) {
+  static std::vector<KernelEntry> f32, f64;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    register_kernels_f32_small(f32);
+    register_kernels_f32_mid(f32);
+    register_kernels_f32_large(f32);
+    register_kernels_f64_small(f64);
+    register_kernels_f64_mid(f64);
+    register_kernels_f64_large(f64);
+  });
+  return precision == GENFFT_CUDA_F32 ? f32 : f64;
+}
+
+// wide = prefer the largest C (column passes), else the smallest (contiguous batched)
+static const KernelEntry* find_kernel(int precision, long long L, bool wide) {
+  const KernelEntry* best = nullptr;
+  for (auto& e : registry(precision)) {
+    if (e.L != L) continue;
+    if (!best || (wide ? e.C > best->C : e.C < best->C)) best = &e;
+  }
+  return best;
+}
+
+static std::mutex g_cfg_mu;
+static std::map<std::pair<int, const void*>, int> g_occupancy;  // (device, func) -> CTAs per SM
+
+static int kernel_occupancy(const KernelEntry* k, int device, int* out) {
+  std::lock_guard<std::mutex> lk(g_cfg_mu);
+  auto key = std::make_pair(device, k->func);
+  auto it = g_occupancy.find(key);
+  if (it != g_occupancy.end()) {
+    *out = it->second;
+    return GENFFT_CUDA_OK;
+  }
+  if (k->smem > 48 * 1024)
+    CU_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+  int n = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k->func, k->threads, k->smem));
+  if (n < 1) return fail(GENFFT_CUDA_ERR_CUDA, "kernel L=%d C=%d cannot be resident (smem %zu)", k->L, k->C, k->smem);
+  g_occupancy[key] = n;
+  *out = n;
+  return GENFFT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// twiddle tables: fp64/long-double computed, stored at the transform's precision
+// (FFTTwiddle.h:46-50 evaluates cos/sin in double and stores T; same contract, exact octant symmetry)
+// ------------------------------------------------------------------------------------------------
+static void unit_root(unsigned long long x, unsigned long long M, long double* c, long double* s) {
+  // (cos, sin)(2*pi*x/M) with x reduced to the first octant so that symmetric entries are exact mirrors
+  x %= M;
+  x *= 8;
+  M *= 8;
+  const unsigned long long q = (4 * x) / M;   // quadrant
+  const unsigned long long r = x - q * (M / 4);  // [0, M/4)
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  long double cc, ss;
+  if (r > M / 8) {
+    const long double th = two_pi * (long double)(M / 4 - r) / (long double)M;
+    cc = sinl(th);
+    ss = cosl(th);
+  } else {
+    const long double th = two_pi * (long double)r / (long double)M;
+    cc = cosl(th);
+    ss = sinl(th);
+  }
+  switch (q) {
+    case 0: *c = cc; *s = ss; break;
+    case 1: *c = -ss; *s = cc; break;
+    case 2: *c = -cc; *s = -ss; break;
+    default: *c = ss; *s = -cc; break;
+  }
+}
+
+static std::mutex g_tw_mu;
+// (device, precision, M, step, count) -> device table of W_M^(e*step), e < count
+static std::map<std::tuple<int, int, long long, long long, long long>, void*> g_tables;
+
+static int twiddle_table(int device, int precision, long long M, long long step, long long count, const void** out) {
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_tuple(device, precision, M, step, count);
+  auto it = g_tables.find(key);
+  if (it != g_tables.end()) {
+    *out = it->second;
+    return GENFFT_CUDA_OK;
+  }
+  const size_t es = elem_size(precision);
+  std::vector<unsigned char> host(es * (size_t)count);
+  for (long long e = 0; e < count; e++) {
+    long double c, s;
+    unit_root((unsigned long long)(e * step), (unsigned long long)M, &c, &s);
+    if (precision == GENFFT_CUDA_F32) {
+      float* p = reinterpret_cast<float*>(host.data()) + 2 * e;
+      p[0] = (float)c;
+      p[1] = (float)-s;
+    } else {
+      double* p = reinterpret_cast<double*>(host.data()) + 2 * e;
+      p[0] = (double)c;
+      p[1] = (double)-s;
+    }
+  }
+  void* d = nullptr;
+  CU_TRY(cudaMalloc(&d, host.size()));
+  CU_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+  g_tables[key] = d;
+  *out = d;
+  return GENFFT_CUDA_OK;
+}
+
+// two-level table for W_M^e, e < M: W = hi[e >> shift] * lo[e & (2^shift - 1)]
+static int two_level_table(int device, int precision, long long M, const void** hi, const void** lo, int* shift) {
+  const int lg = ilog2(M);
+  const int sh = lg <= 12 ? lg : (lg + 1) / 2;
+  int rc = twiddle_table(device, precision, M, 1LL << sh, M >> sh, hi);
+  if (rc) return rc;
+  rc = twiddle_table(device, precision, M, 1, 1LL << sh, lo);
+  if (rc) return rc;
+  *shift = sh;
+  return GENFFT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequence decomposition
+// ------------------------------------------------------------------------------------------------
+static long long max_single_len(int precision, bool wide) {
+  if (wide) return env_int(precision == GENFFT_CUDA_F32 ? "GENFFT_CUDA_WIDE_SINGLE_F32" : "GENFFT_CUDA_WIDE_SINGLE_F64", 4096);
+  return precision == GENFFT_CUDA_F32 ? 16384 : 8192;
+}
+static long long max_pass_len(int precision) {
+  return env_int(precision == GENFFT_CUDA_F32 ? "GENFFT_CUDA_MAXLEN_F32" : "GENFFT_CUDA_MAXLEN_F64",
+                 precision == GENFFT_CUDA_F32 ? 2048 : 2048);
+}
+
+static int build_seq(Seq* seq, int device, int precision, long long N, bool wide) {
+  seq->N = N;
+  seq->wide = wide;
+  seq->passes.clear();
+  if (N == 1) return GENFFT_CUDA_OK;
+  std::vector<long long> lens;
+  if (N <= max_single_len(precision, wide)) {
+    lens.push_back(N);
+  } else {
+    const int lg = ilog2(N);
+    const int lgmax = ilog2(max_pass_len(precision));
+    const int m = (lg + lgmax - 1) / lgmax;
+    int rem = lg;
+    for (int s = 0; s < m; s++) {  // descending, as even as possible
+      int b = (rem + (m - s) - 1) / (m - s);
+      lens.push_back(1LL << b);
+      rem -= b;
+    }
+  }
+  long long Ns = 1;
+  const bool multi = lens.size() > 1;
+  for (size_t s = 0; s < lens.size(); s++) {
+    PassSpec ps;
+    ps.R = lens[s];
+    ps.Ns = Ns;
+    ps.k = find_kernel(precision, ps.R, wide || multi);
+    if (!ps.k) return fail(GENFFT_CUDA_ERR_SIZE, "no kernel for pass length %lld", ps.R);
+    int occ;
+    int rc = kernel_occupancy(ps.k, device, &occ);
+    if (rc) return rc;
+    rc = twiddle_table(device, precision, ps.R, 1, ps.R, &ps.tw_L);
+    if (rc) return rc;
+    if (Ns > 1) {
+      rc = two_level_table(device, precision, Ns * ps.R, &ps.tw_hi, &ps.tw_lo, &ps.tw_shift);
+      if (rc) return rc;
+    }
+    seq->passes.push_back(ps);
+    Ns *= ps.R;
+  }
+  return GENFFT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass emission
+// ------------------------------------------------------------------------------------------------
+static PassParams base_params(const PassSpec& ps, const void* in, void* out, int inverse) {
+  PassParams p;
+  memset(&p, 0, sizeof p);
+  p.in = in;
+  p.out = out;
+  p.n1 = 1;
+  p.n2 = 1;
+  p.out_split_log2 = -1;
+  p.inverse = inverse;
+  p.p_mask = 0xffffffffu;
+  p.tw_L = ps.tw_L;
+  p.tw_hi = ps.tw_hi;
+  p.tw_lo = ps.tw_lo;
+  p.tw_shift = ps.tw_shift;
+  return p;
+}
+
+static uint32_t ceil_div(long long a, long long b) { return (uint32_t)((a + b - 1) / b); }
+
+// `batch` length-N sequences, element stride 1, sequence b at b*dist
+static PassParams emit_1d(const PassSpec& ps, long long N, const void* in, long long in_dist, void* out,
+                          long long out_dist, long long batch, int inverse, bool brev) {
+  PassParams p = base_params(ps, in, out, inverse);
+  const int C = ps.k->C;
+  const long long R = ps.R, Ns = ps.Ns;
+  if (N == R) {  // the whole transform on chip: columns are the transforms
+    p.ncols = (int)batch;
+    p.n2 = ceil_div(batch, C);
+    p.ntiles = p.n2;
+    p.in_stride_i = 1;
+    p.in_stride_c = in_dist;
+    p.out_stride_k = 1;
+    p.out_stride_c = out_dist;
+    p.map_load = p.map_store = 1;
+    if (brev) {
+      p.brev_bits = ilog2(N);
+      p.g_i = 1;
+      p.brev_stride = 1;
+    }
+  } else if (Ns == 1) {  // first pass: y[j*R + k] = DFT_R over i of x[j + i*N/R]
+    const long long cols = N / R;
+    p.ncols = (int)cols;
+    p.n2 = ceil_div(cols, C);
+    p.ntiles = (uint32_t)(batch * p.n2);
+    p.in_t0 = in_dist;
+    p.out_t0 = out_dist;
+    p.in_stride_i = cols;
+    p.in_stride_c = 1;
+    p.out_stride_k = 1;
+    p.out_stride_c = R;
+    p.map_load = 0;
+    p.map_store = 1;
+    if (brev) {
+      p.brev_bits = ilog2(N);
+      p.g_c = 1;
+      p.g_i = cols;
+      p.brev_stride = 1;
+      p.in_stride_c = 0;
+    }
+  } else {  // later pass: j = a*Ns + p;  y[a*Ns*R + p + k*Ns] = DFT_R over i of W^(p*i) x[j + i*N/R]
+    const long long a_cnt = N / (R * Ns);
+    p.n1 = (uint32_t)a_cnt;
+    p.ncols = (int)Ns;
+    p.n2 = ceil_div(Ns, C);
+    p.ntiles = (uint32_t)(batch * a_cnt * p.n2);
+    p.in_t0 = in_dist;
+    p.in_t1 = Ns;
+    p.out_t0 = out_dist;
+    p.out_t1 = Ns * R;
+    p.in_stride_i = N / R;
+    p.in_stride_c = 1;
+    p.out_stride_k = Ns;
+    p.out_stride_c = 1;
+    p.map_load = p.map_store = 0;
+    p.p_c = 1;
+    p.p_mask = (uint32_t)(Ns - 1);
+  }
+  return p;
+}
+
+// length-N transforms down the columns of an (N x cols) array, row pitches in complex elements
+static PassParams emit_col(const PassSpec& ps, long long N, const void* in, long long in_pitch, void* out,
+                           long long out_pitch, long long cols, int inverse, bool brev) {
+  PassParams p = base_params(ps, in, out, inverse);
+  const int C = ps.k->C;
+  const long long R = ps.R, Ns = ps.Ns;
+  p.ncols = (int)cols;
+  p.n2 = ceil_div(cols, C);
+  p.in_stride_c = 1;
+  p.out_stride_c = 1;
+  p.map_load = p.map_store = 0;
+  if (N == R) {
+    p.ntiles = p.n2;
+    p.in_stride_i = in_pitch;
+    p.out_stride_k = out_pitch;
+    if (brev) {
+      p.brev_bits = ilog2(N);
+      p.g_i = 1;
+      p.brev_stride = in_pitch;
+    }
+  } else if (Ns == 1) {
+    p.n1 = (uint32_t)(N / R);
+    p.ntiles = p.n1 * p.n2;
+    p.in_t1 = in_pitch;
+    p.out_t1 = R * out_pitch;
+    p.in_stride_i = (N / R) * in_pitch;
+    p.out_stride_k = out_pitch;
+    if (brev) {
+      p.brev_bits = ilog2(N);
+      p.g_t1 = 1;
+      p.g_i = N / R;
+      p.brev_stride = in_pitch;
+    }
+  } else {
+    const long long a_cnt = N / (R * Ns);
+    p.n1 = (uint32_t)Ns;
+    p.ntiles = (uint32_t)(a_cnt * Ns * p.n2);
+    p.in_t0 = Ns * in_pitch;
+    p.in_t1 = in_pitch;
+    p.out_t0 = Ns * R * out_pitch;
+    p.out_t1 = out_pitch;
+    p.in_stride_i = (N / R) * in_pitch;
+    p.out_stride_k = Ns * out_pitch;
+    p.p_t1 = 1;
+    p.p_c = 0;
+  }
+  return p;
+}
+
+static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p, cudaStream_t stream) {
+  if (p.ntiles == 0) return GENFFT_CUDA_OK;
+  int occ = 1;
+  int rc = kernel_occupancy(ps.k, plan->device, &occ);
+  if (rc) return rc;
+  long long cap = (long long)plan->num_sms * occ;
+  int grid = (int)std::min<long long>(p.ntiles, cap);
+  ps.k->launch(p, grid, stream);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
+template <typename T>
+static int launch_copy_t(const CopyParams& cp, long long batch, cudaStream_t stream) {
+  if (cp.rows <= 0 || cp.cols <= 0 || batch <= 0) return GENFFT_CUDA_OK;
+  dim3 grid((unsigned)std::min<long long>((cp.cols + 255) / 256, 65535), (unsigned)std::min<long long>(cp.rows, 65535),
+            (unsigned)batch);
+  copy_kernel<T><<<grid, 256, 0, stream>>>(cp);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+static int launch_copy(int precision, const CopyParams& cp, long long batch, cudaStream_t stream) {
+  return precision == GENFFT_CUDA_F32 ? launch_copy_t<float>(cp, batch, stream) : launch_copy_t<double>(cp, batch, stream);
+}
+
+static int launch_dit(const Plan* plan, void* out, long long out_dist, const void* in, long long in_dist, int n,
+                      int half, long long batch, bool real_scalar, cudaStream_t stream) {
+  DitParams d;
+  memset(&d, 0, sizeof d);
+  d.in = in;
+  d.out = out;
+  d.in_dist = in_dist;
+  d.out_dist = out_dist;
+  d.n = n;
+  d.half = half;
+  d.batch = (int)batch;
+  d.in_is_real_scalar = real_scalar ? 1 : 0;
+  d.tw_hi = plan->dit_hi;
+  d.tw_lo = plan->dit_lo;
+  d.tw_shift = plan->dit_shift;
+  const int work = n / 4 + 1;
+  dim3 grid((unsigned)std::min((work + 255) / 256, 4096), (unsigned)batch);
+  if (plan->precision == GENFFT_CUDA_F32)
+    dit_kernel<float><<<grid, 256, 0, stream>>>(d);
+  else
+    dit_kernel<double><<<grid, 256, 0, stream>>>(d);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scratch
+// ------------------------------------------------------------------------------------------------
+static int ensure_scratch(Plan* plan, size_t bytes) {
+  std::lock_guard<std::mutex> lk(plan->mu);
+  if (plan->scratch_bytes >= bytes) return GENFFT_CUDA_OK;
+  if (plan->scratch) {
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaFree(plan->scratch));
+    plan->scratch = nullptr;
+    plan->scratch_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&plan->scratch, bytes);
+  if (e != cudaSuccess) return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc(%zu) for scratch failed: %s", bytes, cudaGetErrorString(e));
+  plan->scratch_bytes = bytes;
+  return GENFFT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic multi-pass driver: a chain of steps over buffers IN -> {OUT, SCRATCH} -> OUT
+// ------------------------------------------------------------------------------------------------
+struct View {
+  void* ptr;
+  long long pitch;  // distance between sequences (1D) or row pitch (2D / columns)
+};
+
+struct Step {
+  const PassSpec* ps;
+  long long N;   // sequence length of the Seq this pass belongs to
+  bool col;      // column pass (emit_col) or row/1D pass (emit_1d)
+  bool safe;     // reads and writes the same positions per tile -> may run in place
+  bool brev;
+  bool real_in;
+};
+
+static void seq_steps(const Seq& seq, bool col, std::vector<Step>& steps, bool brev_first, bool real_first) {
+  const size_t m = seq.passes.size();
+  for (size_t s = 0; s < m; s++) {
+    Step st;
+    st.ps = &seq.passes[s];
+    st.N = seq.N;
+    st.col = col;
+    st.safe = (m == 1) || (s == m - 1);
+    st.brev = brev_first && s == 0;
+    st.real_in = real_first && s == 0;
+    if (st.brev || st.real_in) st.safe = st.safe && m == 1;
+    steps.push_back(st);
+  }
+}
+
+// Optional override of the last pass's store: the output bin index is split at 2^part_log2 and the high
+// part selects a peer buffer (fused all-to-all over NVLink) or a block at khi*part_stride.
+struct FinalStore {
+  int part_log2 = -1;
+  void* const* peers = nullptr;
+  int npeers = 0;
+  long long part_stride = 0;
+  long long peer_offset = 0;  // elements added to every peer pointer
+};
+
+// runs `steps`; count = batch (1D) or rows (row passes of 2D); cols = columns for column passes
+static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, long long scratch_pitch,
+                     size_t scratch_elems, long long count, long long cols, int inverse, cudaStream_t stream,
+                     const FinalStore* fs = nullptr) {
+  std::vector<Step> steps(steps_in);
+  if (fs && steps.size() > 1) steps.back().safe = false;  // the last pass writes elsewhere than it reads
+  const size_t es = elem_size(plan->precision);
+  const size_t n = steps.size();
+  // non-in-place steps after the first toggle OUT <-> SCRATCH; choose the first destination so the chain ends in OUT
+  int toggles = 0;
+  for (size_t s = 1; s < n; s++)
+    if (!steps[s].safe) toggles++;
+  bool need_scratch = toggles > 0;
+  const bool aliased = (in.ptr == out.ptr);
+  const bool first_safe = steps[0].safe && in.pitch == out.pitch;
+  const bool copy_in = aliased && !(first_safe && toggles == 0);
+  // aliased input with an unsafe first pass: stage the input into a second scratch region
+  size_t scratch_total = (need_scratch ? scratch_elems : 0) + (copy_in ? scratch_elems : 0);
+  if (scratch_total) {
+    int rc = ensure_scratch(plan, scratch_total * es);
+    if (rc) return rc;
+  }
+  View scr{plan->scratch, scratch_pitch};
+  View cur = in;
+  if (copy_in) {
+    View stage{(char*)plan->scratch + (need_scratch ? scratch_elems * es : 0), scratch_pitch};
+    CopyParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.in = in.ptr;
+    cp.out = stage.ptr;
+    if (steps[0].col) {
+      cp.rows = steps[0].N;
+      cp.cols = cols;
+      cp.in_stride = in.pitch;
+      cp.out_stride = stage.pitch;
+    } else {
+      cp.rows = count;
+      cp.cols = steps[0].N;
+      cp.in_stride = in.pitch;
+      cp.out_stride = stage.pitch;
+    }
+    int rc = launch_copy(plan->precision, cp, 1, stream);
+    if (rc) return rc;
+    cur = stage;
+  }
+  bool dst_is_out = (toggles % 2 == 0);
+  for (size_t s = 0; s < n; s++) {
+    const Step& st = steps[s];
+    View dst;
+    if (s == 0) {
+      dst = dst_is_out ? out : scr;
+    } else if (st.safe) {
+      dst = cur;  // in place
+    } else {
+      dst_is_out = !dst_is_out;
+      dst = dst_is_out ? out : scr;
+    }
+    PassParams p = st.col ? emit_col(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, cols, inverse, st.brev)
+                          : emit_1d(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, count, inverse, st.brev);
+    if (st.real_in) p.in_real = 1;
+    if (fs && s == n - 1) {
+      const long long Ns = (st.N == st.ps->R) ? 1 : st.ps->Ns;
+      const int sh = fs->part_log2 - ilog2(Ns);
+      if (sh < 0) return fail(GENFFT_CUDA_ERR_SIZE, "part size 2^%d smaller than pass stride %lld", fs->part_log2, Ns);
+      p.out_split_log2 = sh;
+      if (fs->peers) {
+        p.use_peers = 1;
+        for (int g = 0; g < fs->npeers && g < kMaxPeers; g++)
+          p.out_peer[g] = (char*)fs->peers[g] + fs->peer_offset * (long long)es;
+      } else {
+        p.out_stride_khi = fs->part_stride;
+      }
+    }
+    int rc = launch_pass(plan, *st.ps, p, stream);
+    if (rc) return rc;
+    cur = dst;
+  }
+  if (cur.ptr != out.ptr) return fail(GENFFT_CUDA_ERR_ARG, "internal: pass chain did not end in the output buffer");
+  (void)es;
+  return GENFFT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan creation
+// ------------------------------------------------------------------------------------------------
+static int new_plan(Plan** out, PlanKind kind, int precision) {
+  if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return fail(GENFFT_CUDA_ERR_ARG, "bad precision %d", precision);
+  int dev, sms;
+  int rc = usable_device(&dev, &sms);
+  if (rc) return rc;
+  Plan* p = new genfft_cuda_plan_s();
+  p->kind = kind;
+  p->precision = precision;
+  p->device = dev;
+  p->num_sms = sms;
+  *out = p;
+  return GENFFT_CUDA_OK;
+}
+
+static const long long kMaxN = 1LL << 27;
+
+}  // namespace genfft_cuda
+
+using namespace genfft_cuda;
+
+
+extern "C" {
+
+const char* genfft_cuda_last_error_string(void) { return g_last_error.c_str(); }
+
+int genfft_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int d = 0; d < n; d++) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+  }
+  return ok;
+}
+
+uint64_t genfft_cuda_launch_count(void) { return g_launches.load(); }
+
+int genfft_cuda_plan_c2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, int64_t batch, int64_t in_dist,
+                            int64_t out_dist) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(n) || n > kMaxN) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld (power of two <= 2^27 required)", (long long)n);
+  if (batch < 1) return fail(GENFFT_CUDA_ERR_ARG, "batch must be >= 1");
+  Plan* p;
+  int rc = new_plan(&p, PLAN_C2C_1D, precision);
+  if (rc) return rc;
+  p->n = n;
+  p->batch = batch;
+  p->in_dist = in_dist ? in_dist : n;
+  p->out_dist = out_dist ? out_dist : n;
+  rc = build_seq(&p->seq, p->device, precision, n, false);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_plan_r2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, int64_t batch, int half,
+                            int64_t in_dist, int64_t out_dist) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(n) || n > 2 * kMaxN) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld", (long long)n);
+  if (batch < 1) return fail(GENFFT_CUDA_ERR_ARG, "batch must be >= 1");
+  Plan* p;
+  int rc = new_plan(&p, PLAN_R2C_1D, precision);
+  if (rc) return rc;
+  p->n = n;
+  p->batch = batch;
+  p->half = half != 0;
+  p->in_dist = in_dist ? in_dist : n;
+  p->out_dist = out_dist ? out_dist : (half ? n / 2 + 1 : n);
+  if (n >= 2 && (p->in_dist & 1)) {
+    delete p;
+    return fail(GENFFT_CUDA_ERR_ARG, "in_dist must be even (the real input is read as packed complex pairs)");
+  }
+  rc = build_seq(&p->seq, p->device, precision, n >= 2 ? n / 2 : 1, false);
+  if (!rc && n >= 8) rc = two_level_table(p->device, precision, n, &p->dit_hi, &p->dit_lo, &p->dit_shift);
+  if (!rc && n < 8) rc = two_level_table(p->device, precision, 8, &p->dit_hi, &p->dit_lo, &p->dit_shift);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_plan_c2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t width, int64_t height) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(width) || !is_pow2(height) || width > kMaxN || height > kMaxN)
+    return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld x %lld", (long long)width, (long long)height);
+  Plan* p;
+  int rc = new_plan(&p, PLAN_C2C_2D, precision);
+  if (rc) return rc;
+  p->width = width;
+  p->height = height;
+  p->n = width * height;
+  rc = build_seq(&p->seq, p->device, precision, width, false);
+  if (!rc) rc = build_seq(&p->seq_v, p->device, precision, height, true);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_plan_vert(genfft_cuda_plan_t* plan, int precision, int64_t n) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(n) || n > kMaxN) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld", (long long)n);
+  Plan* p;
+  int rc = new_plan(&p, PLAN_VERT, precision);
+  if (rc) return rc;
+  p->n = n;
+  rc = build_seq(&p->seq, p->device, precision, n, true);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_plan_dit(genfft_cuda_plan_t* plan, int precision, int64_t n) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  // GetDITImpl asserts n even or n in {1, 2} (generic/fft_dit_impl_generic.inl:120); powers of two here
+  if (!is_pow2(n) || n > 2 * kMaxN) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld", (long long)n);
+  Plan* p;
+  int rc = new_plan(&p, PLAN_DIT, precision);
+  if (rc) return rc;
+  p->n = n;
+  rc = two_level_table(p->device, precision, n >= 8 ? n : 8, &p->dit_hi, &p->dit_lo, &p->dit_shift);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_plan_destroy(genfft_cuda_plan_t plan) {
+  if (!plan) return GENFFT_CUDA_OK;
+  Plan* p = plan;
+  if (p->scratch) cudaFree(p->scratch);
+  if (p->stage_in) cudaFree(p->stage_in);
+  if (p->stage_out) cudaFree(p->stage_out);
+  if (p->streams_ready) {
+    for (auto& s : p->streams)
+      if (s) cudaStreamDestroy(s);
+    for (auto& e : p->events)
+      if (e) cudaEventDestroy(e);
+  }
+  delete plan;
+  return GENFFT_CUDA_OK;
+}
+
+int64_t genfft_cuda_plan_size(genfft_cuda_plan_t plan) { return plan ? plan->n : 0; }
+
+int genfft_cuda_plan_num_passes(genfft_cuda_plan_t plan) {
+  if (!plan) return 0;
+  int n = (int)plan->seq.passes.size() + (int)plan->seq_v.passes.size();
+  if (plan->kind == PLAN_R2C_1D || plan->kind == PLAN_DIT) n += 1;
+  return n;
+}
+
+size_t genfft_cuda_plan_scratch_bytes(genfft_cuda_plan_t plan) { return plan ? plan->scratch_bytes : 0; }
+
+int genfft_cuda_plan_describe(genfft_cuda_plan_t plan, char* buf, size_t buflen) {
+  if (!plan || !buf || !buflen) return fail(GENFFT_CUDA_ERR_ARG, "null argument");
+  std::string s;
+  char tmp[160];
+  auto add_seq = [&](const char* name, const Seq& q) {
+    snprintf(tmp, sizeof tmp, "%s N=%lld:", name, q.N);
+    s += tmp;
+    for (auto& ps : q.passes) {
+      snprintf(tmp, sizeof tmp, " [L=%lld Ns=%lld C=%d thr=%d smem=%zu]", ps.R, ps.Ns, ps.k->C, ps.k->threads, ps.k->smem);
+      s += tmp;
+    }
+    s += ";";
+  };
+  add_seq(plan->kind == PLAN_C2C_2D ? "rows" : "seq", plan->seq);
+  if (plan->kind == PLAN_C2C_2D) add_seq(" cols", plan->seq_v);
+  if (plan->kind == PLAN_R2C_1D) s += " +dit";
+  snprintf(buf, buflen, "%s", s.c_str());
+  return GENFFT_CUDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device-pointer execution
+// ---------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace genfft_cuda {
+int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
+int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStream_t stream, bool brev, bool real_in,
+                      long long batch) {
+  if (!p || p->kind != PLAN_C2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (batch < 0) batch = p->batch;
+  if (p->seq.passes.empty()) {  // n == 1: the transform is the identity
+    if (out == in && !real_in) return GENFFT_CUDA_OK;
+    CopyParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.in = in;
+    cp.out = out;
+    cp.rows = batch;
+    cp.cols = 1;
+    cp.in_stride = p->in_dist;
+    cp.out_stride = p->out_dist;
+    cp.in_real = real_in;
+    return launch_copy(p->precision, cp, 1, stream);
+  }
+  std::vector<Step> steps;
+  seq_steps(p->seq, false, steps, brev, real_in);
+  View vin{const_cast<void*>(in), p->in_dist}, vout{out, p->out_dist};
+  return run_chain(p, steps, vin, vout, p->n, (size_t)p->n * batch, batch, 0, inverse, stream);
+}
+
+int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t st, long long batch) {
+  if (!p || p->kind != PLAN_R2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c_1d plan");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (batch < 0) batch = p->batch;
+  const long long n = p->n;
+  if (n <= 2) {  // no complex sub-transform: the split reads the input directly (FFTReal.h:206-207)
+    return launch_dit(p, out, p->out_dist, in, n == 1 ? p->in_dist : p->in_dist / 2, (int)n, p->half, batch, n == 1, st);
+  }
+  std::vector<Step> steps;
+  seq_steps(p->seq, false, steps, false, false);
+  View vin{const_cast<void*>(in), p->in_dist / 2}, vout{out, p->out_dist};
+  int rc = run_chain(p, steps, vin, vout, n / 2, (size_t)(n / 2) * batch, batch, 0, 0, st);
+  if (rc) return rc;
+  return launch_dit(p, out, p->out_dist, out, p->out_dist, (int)n, p->half, batch, false, st);
+}
+
+bool plan_needs_scratch(const Plan* p) {
+  return p->seq.passes.size() > 2 || p->seq_v.passes.size() > 1;
+}
+}  // namespace genfft_cuda
+
+extern "C" {
+
+int genfft_cuda_exec_c2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, int inverse, void* stream) {
+  return exec_c2c_internal(plan, out, in, inverse, (cudaStream_t)stream, false, false, -1);
+}
+
+int genfft_cuda_exec_c2c_no_scramble_dev(genfft_cuda_plan_t plan, void* inout, int inverse, void* stream) {
+  return exec_c2c_internal(plan, inout, inout, inverse, (cudaStream_t)stream, true, false, -1);
+}
+
+int genfft_cuda_exec_c2c_real_in_dev(genfft_cuda_plan_t plan, void* out, const void* in_real, void* stream) {
+  if (out == in_real) return fail(GENFFT_CUDA_ERR_ARG, "transform_real requires out != in");
+  return exec_c2c_internal(plan, out, in_real, 0, (cudaStream_t)stream, false, true, -1);
+}
+
+int genfft_cuda_exec_r2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream) {
+  return exec_r2c_internal(plan, out, in, (cudaStream_t)stream, -1);
+}
+
+int genfft_cuda_exec_c2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
+                                int64_t in_stride, int inverse, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2C_2D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_2d plan");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "FFT2D::transform requires out != in (fft.h:209)");
+  if (out_stride < p->width || in_stride < p->width) return fail(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<Step> rows, cols;
+  seq_steps(p->seq, false, rows, false, false);
+  seq_steps(p->seq_v, true, cols, false, false);
+  View vin{const_cast<void*>(in), in_stride}, vout{out, out_stride};
+  const size_t elems = (size_t)p->width * p->height;
+  if (rows.empty() && cols.empty()) {
+    CopyParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.in = in;
+    cp.out = out;
+    cp.rows = 1;
+    cp.cols = 1;
+    return launch_copy(p->precision, cp, 1, st);
+  }
+  // one chain over both dimensions: row passes (count = height sequences), then column passes
+  std::vector<Step> steps(rows);
+  steps.insert(steps.end(), cols.begin(), cols.end());
+  return run_chain(p, steps, vin, vout, p->width, elems, p->height, p->width, inverse, st);
+}
+
+int genfft_cuda_exec_vert_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
+                              int64_t in_stride, int64_t cols, int inverse, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_VERT) return fail(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "FFTVert::transform requires out != in (fft.h:141)");
+  if (cols < 0 || out_stride < cols || in_stride < cols) return fail(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
+  if (cols == 0) return GENFFT_CUDA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->seq.passes.empty()) {
+    CopyParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.in = in;
+    cp.out = out;
+    cp.rows = 1;
+    cp.cols = cols;
+    return launch_copy(p->precision, cp, 1, st);
+  }
+  std::vector<Step> steps;
+  seq_steps(p->seq, true, steps, false, false);
+  View vin{const_cast<void*>(in), in_stride}, vout{out, out_stride};
+  return run_chain(p, steps, vin, vout, cols, (size_t)cols * p->n, 0, cols, inverse, st);
+}
+
+int genfft_cuda_exec_vert_no_scramble_dev(genfft_cuda_plan_t plan, void* data, int64_t stride, int64_t cols,
+                                          int inverse, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_VERT) return fail(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  if (!data) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (cols < 0 || stride < cols) return fail(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
+  if (cols == 0 || p->seq.passes.empty()) return GENFFT_CUDA_OK;
+  std::vector<Step> steps;
+  seq_steps(p->seq, true, steps, true, false);
+  View v{data, stride};
+  return run_chain(p, steps, v, v, stride, (size_t)stride * p->n, 0, cols, inverse, (cudaStream_t)stream);
+}
+
+int genfft_cuda_exec_dit_dev(genfft_cuda_plan_t plan, void* out, const void* in, int half, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_DIT) return fail(GENFFT_CUDA_ERR_ARG, "not a dit plan");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  return launch_dit(p, out, 0, in, 0, (int)p->n, half != 0, 1, false, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// distributed 2D building blocks (slab decomposition; the process group lives in genfft_b200/dist.py)
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+static void* const kPeerSentinel = (void*)(uintptr_t)16;
+
+int genfft_cuda_plan_dist_rows(genfft_cuda_plan_t* plan, int precision, int64_t width, int64_t rows, int nparts) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(width) || width > kMaxN || width < 2) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported width %lld", (long long)width);
+  if (!is_pow2(nparts) || nparts > kMaxPeers || nparts > width) return fail(GENFFT_CUDA_ERR_ARG, "nparts must be a power of two <= %d", kMaxPeers);
+  if (rows < 1) return fail(GENFFT_CUDA_ERR_ARG, "rows must be >= 1");
+  Plan* p;
+  int rc = new_plan(&p, PLAN_DIST_ROWS, precision);
+  if (rc) return rc;
+  p->width = width;
+  p->height = rows;
+  p->n = width;
+  p->nparts = nparts;
+  rc = build_seq(&p->seq, p->device, precision, width, false);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_exec_dist_rows_dev(genfft_cuda_plan_t plan, void* out, void* const* out_peers, int64_t part_stride,
+                                   int64_t row0, const void* in, int64_t in_stride, int inverse, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_DIST_ROWS) return fail(GENFFT_CUDA_ERR_ARG, "not a dist_rows plan");
+  if (!in || (!out && !out_peers)) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  const long long Wp = p->width / p->nparts;
+  const size_t es = elem_size(p->precision);
+  FinalStore fs;
+  fs.part_log2 = ilog2(Wp);
+  fs.peers = out_peers;
+  fs.npeers = p->nparts;
+  fs.part_stride = part_stride;
+  fs.peer_offset = row0 * Wp;
+  std::vector<Step> steps;
+  seq_steps(p->seq, false, steps, false, false);
+  View vin{const_cast<void*>(in), in_stride};
+  View vout{out_peers ? kPeerSentinel : (void*)((char*)out + (size_t)(row0 * Wp) * es), Wp};
+  return run_chain(p, steps, vin, vout, p->width, (size_t)p->width * p->height, p->height, 0, inverse,
+                   (cudaStream_t)stream, &fs);
+}
+
+int genfft_cuda_plan_dist_cols(genfft_cuda_plan_t* plan, int precision, int64_t height, int64_t cols, int nparts) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(height) || height > kMaxN || height < 2) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported height %lld", (long long)height);
+  if (!is_pow2(nparts) || nparts > kMaxPeers || nparts > height) return fail(GENFFT_CUDA_ERR_ARG, "nparts must be a power of two <= %d", kMaxPeers);
+  if (cols < 1) return fail(GENFFT_CUDA_ERR_ARG, "cols must be >= 1");
+  Plan* p;
+  int rc = new_plan(&p, PLAN_DIST_COLS, precision);
+  if (rc) return rc;
+  p->width = cols;
+  p->height = height;
+  p->n = height;
+  p->nparts = nparts;
+  rc = build_seq(&p->seq, p->device, precision, height, true);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_exec_dist_cols_dev(genfft_cuda_plan_t plan, void* out, void* const* out_peers, int64_t out_stride,
+                                   int64_t col0, void* data, int64_t stride, int inverse, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_DIST_COLS) return fail(GENFFT_CUDA_ERR_ARG, "not a dist_cols plan");
+  if (!data || (!out && !out_peers)) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  std::vector<Step> steps;
+  seq_steps(p->seq, true, steps, false, false);
+  View vin{data, stride};
+  const size_t elems = (size_t)p->width * p->height;
+  if (!out_peers) {
+    View vout{out, out_stride};
+    return run_chain(p, steps, vin, vout, p->width, elems, 0, p->width, inverse, (cudaStream_t)stream);
+  }
+  FinalStore fs;
+  fs.part_log2 = ilog2(p->height / p->nparts);
+  fs.peers = out_peers;
+  fs.npeers = p->nparts;
+  fs.peer_offset = col0;
+  View vout{kPeerSentinel, out_stride};
+  return run_chain(p, steps, vin, vout, p->width, elems, 0, p->width, inverse, (cudaStream_t)stream, &fs);
+}
+
+// out[b*out_dist + r*out_stride + c] = in[b*in_dist + r*in_stride + c], complex elements (unpack after ncclRecv)
+int genfft_cuda_copy2d_dev(int precision, void* out, int64_t out_stride, int64_t out_dist, const void* in,
+                           int64_t in_stride, int64_t in_dist, int64_t rows, int64_t cols, int64_t batch,
+                           void* stream) {
+  if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return fail(GENFFT_CUDA_ERR_ARG, "bad precision");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  CopyParams cp;
+  memset(&cp, 0, sizeof cp);
+  cp.in = in;
+  cp.out = out;
+  cp.in_stride = in_stride;
+  cp.out_stride = out_stride;
+  cp.in_dist = in_dist;
+  cp.out_dist = out_dist;
+  cp.rows = rows;
+  cp.cols = cols;
+  return launch_copy(precision, cp, batch, (cudaStream_t)stream);
+}
+
+int genfft_cuda_malloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(GENFFT_CUDA_ERR_ARG, "null");
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return GENFFT_CUDA_OK;
+}
+int genfft_cuda_free(void* ptr) {
+  CU_TRY(cudaFree(ptr));
+  return GENFFT_CUDA_OK;
+}
+int genfft_cuda_ipc_get_handle(void* ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle, &h, 64);
+  return GENFFT_CUDA_OK;
+}
+int genfft_cuda_ipc_open_handle(void** ptr, const unsigned char handle[64]) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GENFFT_CUDA_OK;
+}
+int genfft_cuda_ipc_close_handle(void* ptr) {
+  CU_TRY(cudaIpcCloseMemHandle(ptr));
+  return GENFFT_CUDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// Host-side plan structures of libgenfft_cuda (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "registry.h"
+
+namespace genfft_cuda {
+
+enum PlanKind { PLAN_C2C_1D, PLAN_R2C_1D, PLAN_C2C_2D, PLAN_VERT, PLAN_DIT, PLAN_DIST_ROWS, PLAN_DIST_COLS };
+
+// one Stockham pass of a length-N sequence: radix R = kernel length, Ns = product of earlier radices
+struct PassSpec {
+  const KernelEntry* k = nullptr;
+  long long R = 1, Ns = 1;
+  const void* tw_L = nullptr;
+  const void* tw_hi = nullptr;  // inter-pass twiddle W_{Ns*R} (null for the first pass)
+  const void* tw_lo = nullptr;
+  int tw_shift = 0;
+};
+
+// decomposition of one length-N transform
+struct Seq {
+  long long N = 1;
+  std::vector<PassSpec> passes;  // empty when N == 1
+  bool wide = false;             // built for column (strided) use
+};
+
+struct Plan {
+  PlanKind kind;
+  int precision;
+  int device;
+  int num_sms;
+  long long n = 0, batch = 1, in_dist = 0, out_dist = 0;
+  int half = 0;
+  long long width = 0, height = 0;
+  int nparts = 1;
+  Seq seq;    // 1D sequence (c2c_1d: n; r2c: n/2; 2d: rows (width); vert: n)
+  Seq seq_v;  // 2D: columns (height)
+  // DIT twiddles (W_n two-level)
+  const void* dit_hi = nullptr;
+  const void* dit_lo = nullptr;
+  int dit_shift = 0;
+  // scratch (device), lazily grown
+  std::mutex mu;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  size_t scratch_need = 0;  // upper bound known at plan time (0 if none / depends on exec args)
+  // host-pointer staging
+  void* stage_in = nullptr;
+  void* stage_out = nullptr;
+  size_t stage_in_bytes = 0, stage_out_bytes = 0;
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t events[8] = {};
+  bool streams_ready = false;
+};
+
+}  // namespace genfft_cuda
+
+// the opaque C handle is the plan itself
+struct genfft_cuda_plan_s : genfft_cuda::Plan {};
+
+namespace genfft_cuda {
+
+size_t elem_size(int precision);
+int set_error(int code, const char* msg);
+int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStream_t stream, bool brev, bool real_in,
+                      long long batch);
+int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t stream, long long batch);
+bool plan_needs_scratch(const Plan* p);
+
+}  // namespace genfft_cuda

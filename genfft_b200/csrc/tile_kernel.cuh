@@ -1,0 +1,273 @@
+// The one butterfly kernel of the engine: a CTA transforms a tile of C independent length-L
+// sequences ("columns") entirely on chip -- registers for the radix-P butterflies, padded shared
+// memory for the exchanges between radix stages (Stockham auto-sort, so no bit-reversal pass
+// exists anywhere: the reference's scramble, include/genFFT/FFTUtil.h:37-83, which is 20-80 % of
+// its run time, has no counterpart here).
+//
+// Everything the hot path does is this kernel with different addressing:
+//   * batched contiguous 1D (FFT<T>::transform, fft.h:80-85): columns = transforms, lanes run along
+//     the sequence (map B) so global loads/stores are fully coalesced;
+//   * column / strided passes (FFTVert, fft.h:145-150; the column pass of FFT2D, fft.h:216-217;
+//     every pass of a large multi-pass 1D transform): columns are adjacent in memory, lanes run
+//     across columns (map A) so each row of the tile is one contiguous segment;
+//   * multi-pass large N: the Stockham inter-pass twiddle W_M^(p*i) is fused into the load, the
+//     output permutation into the store;
+//   * distributed 2D: the store can scatter the tile over up to 8 peer GPUs' buffers (NVLink
+//     stores), fusing the all-to-all transpose into the producing pass.
+#pragma once
+#include <cstdint>
+#include "radix.cuh"
+
+namespace genfft_cuda {
+
+constexpr int kMaxPeers = 8;
+
+struct PassParams {
+  const void* in;
+  void* out;
+  void* out_peer[kMaxPeers];  // used when out_split_log2 >= 0 && use_peers
+  // tile enumeration: tile -> (t0, t1, t2), t2 fastest; t2 enumerates blocks of C columns
+  uint32_t n1, n2;
+  uint32_t ntiles;
+  long long in_t0, in_t1;    // element offsets per tile index (t2 handled through the column index)
+  long long out_t0, out_t1;
+  long long in_stride_i;     // between consecutive sequence elements
+  long long in_stride_c;     // between adjacent columns
+  long long out_stride_k;    // between consecutive output bins (low part when split)
+  long long out_stride_c;
+  long long out_stride_khi;  // stride of (k >> out_split_log2) when out_split_log2 >= 0
+  int out_split_log2;        // -1: plain affine output addressing
+  int use_peers;             // 1: (k >> out_split_log2) selects out_peer[], out_stride_khi ignored
+  int ncols;                 // valid columns along t2*C + c (tail tiles are masked)
+  int map_load, map_store;   // 0 = lanes across columns (A), 1 = lanes along the sequence (B)
+  int inverse;               // conjugate on load and on store
+  int in_real;               // input is real scalars (imag = 0); FFT<T>::transform_real, fft.h:90-94
+  // bit-reversed input (transform_no_scramble contract, fft.h:69-73 / 132-136):
+  //   offset = brev(t1*g_t1 + col*g_c + idx*g_i, brev_bits) * brev_stride + t0*in_t0 + col*in_stride_c
+  int brev_bits;
+  long long g_t1, g_c, g_i, brev_stride;
+  // inter-pass Stockham twiddle W_M^(p*idx), p = t1*p_t1 + col*p_c, two-level table
+  const void* tw_hi;
+  const void* tw_lo;
+  int tw_shift;     // e = p*idx ; W = tw_hi[e >> tw_shift] * tw_lo[e & ((1<<tw_shift)-1)]
+  int p_t1, p_c;
+  uint32_t p_mask;  // p &= p_mask
+  // on-chip stage twiddles W_L^e, e < L
+  const void* tw_L;
+};
+
+__host__ __device__ constexpr int stage_radix(int L, int P, int s) {
+  int rem = L;
+  for (int k = 0; k < s; k++) rem /= P;
+  return rem >= P ? P : rem;
+}
+__host__ __device__ constexpr int num_stages(int L, int P) {
+  int n = 0, rem = L;
+  while (rem > 1) { rem = rem >= P ? rem / P : 1; n++; }
+  return n;
+}
+__host__ __device__ constexpr int stage_ns(int L, int P, int s) {
+  int ns = 1;
+  for (int k = 0; k < s; k++) ns *= stage_radix(L, P, k);
+  return ns;
+}
+
+// one padding element per 16: conflict-free for the stride-r scatters of every radix <= 16
+__host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int tile_pitch(int L) { return pad_idx(L) | 1; }
+
+template <typename T, int L, int P, int C>
+struct TileKernel {
+  static constexpr int TN = L / P;
+  static constexpr int THREADS = TN * C;
+  static constexpr int NST = num_stages(L, P);
+  static constexpr int PITCH = tile_pitch(L);
+  static constexpr size_t SMEM_BYTES = NST > 1 ? sizeof(cpx<T>) * (size_t)PITCH * C : 0;
+  using V = typename vec2<T>::type;
+
+  static __device__ __forceinline__ uint32_t brev(uint32_t v, int bits) { return __brev(v) >> (32 - bits); }
+
+  struct Tile {
+    long long in_off, out_off;
+    uint32_t p_base;
+    uint32_t col0;
+    long long g_base;
+  };
+
+  static __device__ __forceinline__ Tile decode(const PassParams& prm, uint32_t tile) {
+    uint32_t t2 = tile % prm.n2;
+    uint32_t t01 = tile / prm.n2;
+    uint32_t t1 = t01 % prm.n1;
+    uint32_t t0 = t01 / prm.n1;
+    Tile t;
+    t.col0 = t2 * C;
+    t.in_off = (long long)t0 * prm.in_t0 + (long long)t1 * prm.in_t1;
+    t.out_off = (long long)t0 * prm.out_t0 + (long long)t1 * prm.out_t1;
+    t.p_base = t1 * (uint32_t)prm.p_t1;
+    t.g_base = (long long)t1 * prm.g_t1;
+    if (prm.brev_bits) t.in_off = (long long)t0 * prm.in_t0;
+    return t;
+  }
+
+  static __device__ __forceinline__ void load(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {
+    const uint32_t col = t.col0 + c;
+    const bool valid = col < (uint32_t)prm.ncols;
+    const long long base = t.in_off + (long long)col * prm.in_stride_c;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int idx = u + i * TN;
+      long long off;
+      if (prm.brev_bits) {
+        uint32_t g = (uint32_t)(t.g_base + (long long)col * prm.g_c + (long long)idx * prm.g_i);
+        off = base + (long long)brev(g, prm.brev_bits) * prm.brev_stride;
+      } else {
+        off = base + (long long)idx * prm.in_stride_i;
+      }
+      if (valid) {
+        if (prm.in_real) {
+          x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], T(0));
+        } else {
+          V v = reinterpret_cast<const V*>(prm.in)[off];
+          x[i] = cpx<T>(v.x, v.y);
+        }
+      } else {
+        x[i] = cpx<T>(T(0), T(0));
+      }
+    }
+    if (prm.inverse) {
+#pragma unroll
+      for (int i = 0; i < P; i++) x[i].y = -x[i].y;
+    }
+    if (prm.tw_hi) {
+      const uint32_t p = (t.p_base + col * (uint32_t)prm.p_c) & prm.p_mask;
+      const V* hi = reinterpret_cast<const V*>(prm.tw_hi);
+      const V* lo = reinterpret_cast<const V*>(prm.tw_lo);
+      const uint32_t lomask = (1u << prm.tw_shift) - 1u;
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        const uint32_t e = p * (uint32_t)(u + i * TN);
+        V a = __ldg(hi + (e >> prm.tw_shift));
+        V b = __ldg(lo + (e & lomask));
+        cpx<T> w = cmul(cpx<T>(a.x, a.y), cpx<T>(b.x, b.y));
+        x[i] = cmul(x[i], w);
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void store(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {
+    const uint32_t col = t.col0 + c;
+    if (col >= (uint32_t)prm.ncols) return;
+    const long long base = t.out_off + (long long)col * prm.out_stride_c;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int k = u + i * TN;
+      V v;
+      v.x = x[i].x;
+      v.y = prm.inverse ? -x[i].y : x[i].y;
+      if (prm.out_split_log2 < 0) {
+        reinterpret_cast<V*>(prm.out)[base + (long long)k * prm.out_stride_k] = v;
+      } else {
+        const int khi = k >> prm.out_split_log2;
+        const int klo = k & ((1 << prm.out_split_log2) - 1);
+        if (prm.use_peers) {
+          reinterpret_cast<V*>(prm.out_peer[khi])[base + (long long)klo * prm.out_stride_k] = v;
+        } else {
+          reinterpret_cast<V*>(prm.out)[base + (long long)klo * prm.out_stride_k + (long long)khi * prm.out_stride_khi] = v;
+        }
+      }
+    }
+  }
+
+  // radix stage S on registers; scatters to shared memory unless it is the last stage
+  template <int S>
+  static __device__ __forceinline__ void stage(const PassParams& prm, cpx<T> (&x)[P], cpx<T>* sm, int u) {
+    constexpr int R = stage_radix(L, P, S);
+    constexpr int NS = stage_ns(L, P, S);
+    constexpr int M = P / R;  // butterflies per thread
+    constexpr bool LAST = (S == NST - 1);
+    const V* twL = reinterpret_cast<const V*>(prm.tw_L);
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+      const int j = u + m * TN;
+      const int p = j & (NS - 1);
+      cpx<T> y[R];
+#pragma unroll
+      for (int q = 0; q < R; q++) y[q] = x[m + q * M];
+      if (NS > 1) {
+#pragma unroll
+        for (int q = 1; q < R; q++) {
+          V w = __ldg(twL + (p * q) * (L / (NS * R)));
+          y[q] = cmul(y[q], cpx<T>(w.x, w.y));
+        }
+      }
+      RegDFT<R>::run(y);
+      if (LAST) {
+        // bin k -> position p + k*NS = u + (m + k*M)*TN  -> register slot m + k*M
+#pragma unroll
+        for (int s = 0; s < R; s++) x[m + RegDFT<R>::out_bin(s) * M] = y[s];
+      } else {
+        const int base = (j - p) * R + p;
+#pragma unroll
+        for (int s = 0; s < R; s++) {
+          const int pos = base + RegDFT<R>::out_bin(s) * NS;
+          V v;
+          v.x = y[s].x;
+          v.y = y[s].y;
+          reinterpret_cast<V*>(sm)[pad_idx(pos)] = v;
+        }
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void gather(cpx<T> (&x)[P], const cpx<T>* sm, int u) {
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      V v = reinterpret_cast<const V*>(sm)[pad_idx(u + i * TN)];
+      x[i] = cpx<T>(v.x, v.y);
+    }
+  }
+
+  template <int S>
+  static __device__ __forceinline__ void run_stages(const PassParams& prm, cpx<T> (&x)[P], cpx<T>* smem,
+                                                     int& c, int& u, int c_st, int u_st) {
+    if constexpr (S < NST) {
+      stage<S>(prm, x, smem + (size_t)c * PITCH, u);
+      if constexpr (S < NST - 1) {
+        __syncthreads();
+        if constexpr (S == NST - 2) {  // switch to the store mapping before the last stage
+          c = c_st;
+          u = u_st;
+        }
+        gather(x, smem + (size_t)c * PITCH, u);
+        if constexpr (S < NST - 2) __syncthreads();  // buffer is rewritten by the next scatter
+      }
+      run_stages<S + 1>(prm, x, smem, c, u, c_st, u_st);
+    }
+  }
+
+  static __device__ __forceinline__ void body(const PassParams& prm, cpx<T>* smem) {
+    const int tid = threadIdx.x;
+    const int c_ld = prm.map_load ? tid / TN : tid % C;
+    const int u_ld = prm.map_load ? tid % TN : tid / C;
+    const int c_st = prm.map_store ? tid / TN : tid % C;
+    const int u_st = prm.map_store ? tid % TN : tid / C;
+    cpx<T> x[P];
+    for (uint32_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+      Tile t = decode(prm, tile);
+      load(prm, t, c_ld, u_ld, x);
+      int c = c_ld, u = u_ld;
+      run_stages<0>(prm, x, smem, c, u, c_st, u_st);
+      store(prm, t, c, u, x);
+      if (NST > 1) __syncthreads();  // next tile's first scatter must not overtake this tile's gathers
+    }
+  }
+};
+
+template <typename T, int L, int P, int C>
+__global__ void __launch_bounds__(TileKernel<T, L, P, C>::THREADS)
+fft_tile_kernel(const __grid_constant__ PassParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileKernel<T, L, P, C>::body(prm, reinterpret_cast<cpx<T>*>(smem_raw));
+}
+
+}  // namespace genfft_cuda

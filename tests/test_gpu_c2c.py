@@ -1,0 +1,216 @@
+"""Parity of the CUDA 1D complex path (through the C ABI) against genFFT's CPU output.
+
+Mirrors the structure of the reference's TestFFT_Pow2 (test/fft_test_impl.h:35-58) and its size loops
+(test/test_dispatch.cpp:45-65, test/test_fft.cpp:41-66): forward vs reference, inverse vs reference,
+round trip; tolerance is north_star's rel-L2 <= 1e-6*log2N (float) / 1e-14*log2N (double), and the
+reference's own absolute FFT_Eps (test/test_util.h:62-72) is checked as well.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import genfft_b200 as g  # noqa: E402
+
+CPX = {np.float32: np.complex64, np.float64: np.complex128}
+
+
+def fft_eps(n, dt):
+    return (1e-5 + n * 1e-8) if dt == np.float32 else (1e-8 + n * 1e-12)
+
+
+def rand_cpx(rng, shape, dt):
+    return (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(CPX[dt])
+
+
+def gpu_c2c(x, inv=False, batch=1):
+    n = x.shape[-1]
+    plan = g.FFT(n, x.real.dtype, batch=batch)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty_like(d_in)
+    plan.transform(d_out, d_in, inv)
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy(), plan
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("lg", list(range(0, 21)))
+def test_c2c_pow2_vs_reference(comparand, checkers, dt, lg):
+    n = 1 << lg
+    ref = checkers[0]
+    x = ref.dummy_complex(n, dt) if ref is not None else rand_cpx(np.random.default_rng(lg), n, dt)
+    want_f = comparand.c2c(x, False)
+    want_i = comparand.c2c(want_f, True)
+    got_f, plan = gpu_c2c(x, False)
+    assert plan.size() == n and bool(plan)
+    tol = oracle.tolerance(n, dt)
+    assert oracle.rel_l2(got_f, want_f) <= tol, plan.describe()
+    got_i, _ = gpu_c2c(want_f, True)
+    assert oracle.rel_l2(got_i, want_i) <= tol
+    # the reference's own acceptance: absolute eps per element, and the round trip inv(fwd(x))/n == x
+    eps = fft_eps(n, dt)
+    assert np.max(np.abs(got_f - want_f)) <= eps
+    back, _ = gpu_c2c(got_f, True)
+    assert np.max(np.abs(back / n - x)) <= eps
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,batch", [(2, 5), (16, 300), (64, 33), (256, 17), (1024, 9), (4096, 64), (4096, 7),
+                                     (8192, 3), (1 << 15, 3), (1 << 17, 2)])
+def test_c2c_batched(comparand, dt, n, batch):
+    rng = np.random.default_rng(n + batch)
+    x = rand_cpx(rng, (batch, n), dt)
+    for inv in (False, True):
+        want = comparand.c2c_batch(x, inv)
+        got, plan = gpu_c2c(x, inv, batch=batch)
+        assert oracle.rel_l2(got, want) <= oracle.tolerance(n, dt), plan.describe()
+        for b in (0, batch - 1):
+            assert oracle.rel_l2(got[b], want[b]) <= oracle.tolerance(n, dt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_c2c_batched_with_dist(comparand, dt):
+    n, batch, in_dist, out_dist = 512, 6, 520, 600
+    rng = np.random.default_rng(1)
+    buf = rand_cpx(rng, batch * in_dist, dt)
+    plan = g.FFT(n, dt, batch=batch, in_dist=in_dist, out_dist=out_dist)
+    d_in = torch.from_numpy(buf).cuda()
+    d_out = torch.full((batch * out_dist,), 7 + 5j, dtype=d_in.dtype, device="cuda")
+    plan.transform(d_out, d_in)
+    got = d_out.cpu().numpy().reshape(batch, out_dist)
+    for b in range(batch):
+        want = comparand.c2c(buf[b * in_dist:b * in_dist + n].copy())
+        assert oracle.rel_l2(got[b, :n], want) <= oracle.tolerance(n, dt)
+        assert np.all(got[b, n:] == 7 + 5j)  # gaps are not touched
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 8, 1024, 4096, 1 << 16])
+def test_c2c_host_pointers(comparand, dt, n):
+    """The literal drop-in: host buffers in, host buffers out (FFT<T>::transform on std::complex<T>*)."""
+    rng = np.random.default_rng(n)
+    x = rand_cpx(rng, n, dt)
+    out = np.empty_like(x)
+    plan = g.FFT(n, dt)
+    plan.forward(out, x)
+    assert oracle.rel_l2(out, comparand.c2c(x)) <= oracle.tolerance(n, dt)
+    back = np.empty_like(x)
+    plan.inverse(back, out)
+    assert np.max(np.abs(back / n - x)) <= fft_eps(n, dt)
+
+
+def test_c2c_host_pointers_batched_chunked(comparand, monkeypatch):
+    monkeypatch.setenv("GENFFT_CUDA_HOST_CHUNK_MB", "1")  # force several pipelined chunks
+    n, batch = 4096, 100
+    x = rand_cpx(np.random.default_rng(5), (batch, n), np.float32)
+    out = np.empty_like(x)
+    g.FFT(n, np.float32, batch=batch).forward(out, x)
+    assert oracle.rel_l2(out, comparand.c2c_batch(x)) <= oracle.tolerance(n, np.float32)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 4, 64, 4096, 1 << 15])
+def test_transform_no_scramble(comparand, dt, n):
+    """FFT<T>::transform_no_scramble (fft.h:69-73): bit-reversed input, in place, natural output."""
+    rng = np.random.default_rng(n + 3)
+    x = rand_cpx(rng, n, dt)
+    want = comparand.c2c_no_scramble(x)
+    plan = g.FFT(n, dt)
+    d = torch.from_numpy(x.copy()).cuda()
+    plan.transform_no_scramble(d)
+    assert oracle.rel_l2(d.cpu().numpy(), want) <= oracle.tolerance(n, dt)
+    h = x.copy()
+    plan.transform_no_scramble(h, inv=True)
+    assert oracle.rel_l2(h, comparand.c2c_no_scramble(x, True)) <= oracle.tolerance(n, dt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 16, 1024, 1 << 15])
+def test_transform_real(comparand, dt, n):
+    """FFT<T>::transform_real (fft.h:90-94)."""
+    x = np.random.default_rng(n).uniform(-1, 1, n).astype(dt)
+    plan = g.FFT(n, dt)
+    d_out = torch.empty(n, dtype=torch.complex64 if dt == np.float32 else torch.complex128, device="cuda")
+    plan.transform_real(d_out, torch.from_numpy(x).cuda())
+    assert oracle.rel_l2(d_out.cpu().numpy(), comparand.transform_real(x)) <= oracle.tolerance(n, dt)
+
+
+def test_in_place_device(comparand):
+    for n in (4096, 1 << 16):
+        x = rand_cpx(np.random.default_rng(n), n, np.float32)
+        d = torch.from_numpy(x).cuda()
+        g.FFT(n, np.float32).transform(d, d)
+        assert oracle.rel_l2(d.cpu().numpy(), comparand.c2c(x)) <= oracle.tolerance(n, np.float32)
+
+
+def test_errors():
+    with pytest.raises(g.GenfftCudaError):
+        g.FFT(3)  # not a power of two (reference: assert(!"unsupported size"))
+    with pytest.raises(g.GenfftCudaError):
+        g.FFT(0)
+    empty = g.FFT()
+    assert not empty and empty.size() == 0
+    with pytest.raises(g.GenfftCudaError):
+        empty.transform(np.zeros(4, np.complex64), np.zeros(4, np.complex64))
+    plan = g.FFT(8)
+    x = np.zeros(8, np.complex64)
+    with pytest.raises(g.GenfftCudaError):
+        plan.transform(x, x)  # out != in on the host path, like the reference
+    with pytest.raises(ValueError):
+        plan.transform(np.zeros(4, np.complex64), x)
+    with pytest.raises(TypeError):
+        plan.transform(np.zeros(8, np.complex128), np.zeros(8, np.complex128))
+
+
+@pytest.mark.parametrize("n,dt", [(1 << 22, np.float32), (1 << 23, np.float32), (1 << 22, np.float64)])
+def test_c2c_large(comparand, n, dt):
+    x = rand_cpx(np.random.default_rng(9), n, dt)
+    got, plan = gpu_c2c(x)
+    assert oracle.rel_l2(got, comparand.c2c(x)) <= oracle.tolerance(n, dt), plan.describe()
+
+
+def test_c3_2pow24_double(checkers):
+    """BASELINE config C3: N = 2^24 double, against the reference's own kernels via the factory hook."""
+    ref = checkers[0]
+    if ref is None:
+        pytest.skip("compiled reference not present")
+    n = 1 << 24
+    x = rand_cpx(np.random.default_rng(24), n, np.float64)
+    got, plan = gpu_c2c(x)
+    assert oracle.rel_l2(got, ref.c2c(x)) <= oracle.tolerance(n, np.float64), plan.describe()
+    back, _ = gpu_c2c(got, True)
+    assert np.max(np.abs(back / n - x)) <= 1e-8 + n * 1e-12
+
+
+def test_c2_full_size_properties(comparand):
+    """BASELINE config C2 at full size (N=4096 x 2^16, fp32): sampled rows vs the reference, round trip,
+    linearity and Parseval over the whole batch."""
+    n, batch = 4096, 1 << 16
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.view_as_complex(torch.rand((batch, n, 2), generator=gen, device="cuda") * 2 - 1)
+    plan = g.FFT(n, np.float32, batch=batch)
+    y = torch.empty_like(x)
+    plan.transform(y, x)
+    rows = [0, 1, 4095, 32768, batch - 1]
+    xs = x[rows].cpu().numpy()
+    ys = y[rows].cpu().numpy()
+    for r in range(len(rows)):
+        assert oracle.rel_l2(ys[r], comparand.c2c(xs[r])) <= oracle.tolerance(n, np.float32)
+    # Parseval: sum |X|^2 = n * sum |x|^2
+    ex = (x.abs().double() ** 2).sum().item()
+    ey = (y.abs().double() ** 2).sum().item()
+    assert abs(ey / (n * ex) - 1) < 1e-5
+    # round trip
+    z = torch.empty_like(x)
+    plan.transform(z, y, True)
+    assert (z / n - x).abs().max().item() <= fft_eps(n, np.float32)
+    # linearity: F(x + 2*roll(x)) == F(x) + 2*F(roll(x)) along the batch axis
+    x2 = x + 2 * torch.roll(x, 1, 0)
+    y2 = torch.empty_like(x)
+    plan.transform(y2, x2)
+    want = y + 2 * torch.roll(y, 1, 0)
+    rel = ((y2 - want).abs().double() ** 2).sum().sqrt().item() / (want.abs().double() ** 2).sum().sqrt().item()
+    assert rel <= oracle.tolerance(n, np.float32)

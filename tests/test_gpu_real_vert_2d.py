@@ -1,0 +1,209 @@
+"""Parity of the real-input, DIT, vertical and 2D CUDA paths against genFFT's CPU output.
+
+Structure follows the reference's TestRealFFT_Pow2 / TestDIT_Pow2 / TestFFTVert_Pow2
+(test/fft_test_impl.h:60-131) and their size lists (test/test_real_fft.cpp:42-67, test/test_dit.cpp:45-67,
+test/test_dispatch.cpp:84-126).  FFT2D has no test in the reference; it is checked against the compiled
+reference itself and numpy's fft2.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import genfft_b200 as g  # noqa: E402
+
+CPX = {np.float32: np.complex64, np.float64: np.complex128}
+TCPX = {np.float32: torch.complex64, np.float64: torch.complex128}
+FILL = 43 + 21j  # the reference's corruption sentinel (test/fft_test_impl.h:88)
+
+
+def rand_cpx(rng, shape, dt):
+    return (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(CPX[dt])
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("half", [True, False])
+@pytest.mark.parametrize("lg", [0, 1, 2, 3, 4, 5, 6, 8, 10, 12, 13, 14, 16, 18, 20, 22])
+def test_real_fft_vs_reference(comparand, checkers, dt, half, lg):
+    n = 1 << lg
+    ref = checkers[0]
+    x = ref.dummy_real(n, dt) if ref is not None else np.random.default_rng(lg).uniform(-1, 1, n).astype(dt)
+    want = comparand.r2c(x, half, fill=FILL)
+    plan = g.RealFFT(n, dt, half=half)
+    d_out = torch.full((max(n, 1),), FILL, dtype=TCPX[dt], device="cuda")
+    plan.forward(d_out, torch.from_numpy(x).cuda(), half)
+    got = d_out.cpu().numpy()
+    limit = 1 if n == 1 else (n // 2 + 1 if half else n)
+    assert oracle.rel_l2(got[:limit], want[:limit]) <= oracle.tolerance(n, dt), plan.describe()
+    eps = (1e-5 + n * 1e-8) if dt == np.float32 else (1e-8 + n * 1e-12)
+    assert np.max(np.abs(got[:limit] - want[:limit])) <= eps
+    # "Corruption detected": nothing may be written past n/2+1 when half (test/fft_test_impl.h:102-105)
+    assert np.all(got[limit:] == FILL)
+    # host-pointer path
+    h_out = np.full(max(n, 1), FILL, dtype=CPX[dt])
+    plan.forward(h_out, x)
+    assert oracle.rel_l2(h_out[:limit], want[:limit]) <= oracle.tolerance(n, dt)
+    assert np.all(h_out[limit:] == FILL)
+
+
+@pytest.mark.parametrize("n,batch", [(8, 5), (1024, 7), (1 << 14, 3), (1 << 16, 2)])
+def test_real_fft_batched(comparand, n, batch):
+    x = np.random.default_rng(n).uniform(-1, 1, (batch, n)).astype(np.float32)
+    plan = g.RealFFT(n, np.float32, half=True, batch=batch)
+    d_out = torch.empty((batch, n // 2 + 1), dtype=torch.complex64, device="cuda")
+    plan.forward(d_out, torch.from_numpy(x).cuda())
+    got = d_out.cpu().numpy()
+    for b in range(batch):
+        want = comparand.r2c(x[b], True)[: n // 2 + 1]
+        assert oracle.rel_l2(got[b], want) <= oracle.tolerance(n, np.float32)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("in_place", [False, True])
+@pytest.mark.parametrize("lg", [1, 2, 3, 4, 6, 10, 14, 18, 20])
+def test_dit_vs_reference(comparand, dt, in_place, lg):
+    """DIT::apply of the n/2-point FFT equals the n-point FFT of the real signal (TestDIT_Pow2)."""
+    n = 1 << lg
+    x = np.random.default_rng(lg).uniform(-1, 1, n).astype(dt)
+    z = comparand.c2c(x.view(CPX[dt])) if n >= 4 else x.view(CPX[dt]).copy()
+    want = comparand.dit(z, n, half=False, in_place=in_place)
+    plan = g.DIT(n, dt)
+    d_in = torch.zeros(n, dtype=TCPX[dt], device="cuda")
+    d_in[: n // 2] = torch.from_numpy(z).cuda()
+    d_out = d_in if in_place else torch.zeros_like(d_in)
+    plan.apply(d_out, d_in, False)
+    got = d_out.cpu().numpy()
+    assert oracle.rel_l2(got, want) <= oracle.tolerance(n, dt)
+    full = comparand.c2c(x.astype(CPX[dt]))
+    assert oracle.rel_l2(got, full) <= oracle.tolerance(n, dt)
+
+
+# the reference's own (nfft, cols) list: test/test_dispatch.cpp:96-120
+VERT_CASES = [(1, 1), (2, 1), (4, 1), (2, 3), (4, 7), (8, 33), (16, 47), (32, 63), (64, 5), (128, 767), (256, 999),
+              (512, 1023), (1024, 31), (4096, 17), (8192, 3), (16384, 2), (65536, 31)]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,cols", VERT_CASES)
+def test_vert_vs_reference(comparand, dt, n, cols):
+    if dt == np.float64 and n * cols > (1 << 21):
+        pytest.skip("kept small in double to bound CPU time")
+    x = rand_cpx(np.random.default_rng(n + cols), (n, cols), dt)
+    plan = g.FFTVert(n, dt)
+    for inv in (False, True):
+        want = comparand.vert(x, inv)
+        d_out = torch.empty((n, cols), dtype=TCPX[dt], device="cuda")
+        plan.transform(d_out, torch.from_numpy(x).cuda(), cols, inv=inv)
+        assert oracle.rel_l2(d_out.cpu().numpy(), want) <= oracle.tolerance(n, dt), plan.describe()
+
+
+def test_vert_strided_and_host(comparand):
+    n, cols, in_stride, out_stride = 256, 37, 40, 64
+    x = rand_cpx(np.random.default_rng(2), (n, in_stride), np.float32)
+    want = comparand.vert(x, False, cols=cols)[:, :cols]
+    plan = g.FFTVert(n, np.float32)
+    d_out = torch.full((n, out_stride), FILL, dtype=torch.complex64, device="cuda")
+    plan.transform(d_out, torch.from_numpy(x).cuda(), cols, out_stride=out_stride, in_stride=in_stride)
+    got = d_out.cpu().numpy()
+    assert oracle.rel_l2(got[:, :cols], want) <= oracle.tolerance(n, np.float32)
+    assert np.all(got[:, cols:] == FILL)
+    h_out = np.full((n, out_stride), FILL, dtype=np.complex64)
+    plan.transform(h_out, x, cols, out_stride=out_stride, in_stride=in_stride)
+    assert oracle.rel_l2(h_out[:, :cols], want) <= oracle.tolerance(n, np.float32)
+
+
+@pytest.mark.parametrize("n,cols", [(8, 5), (256, 33), (8192, 4)])
+def test_vert_no_scramble(comparand, n, cols):
+    """FFTVert::transform_no_scramble (fft.h:132-136): rows arrive bit-reversed, in place."""
+    x = rand_cpx(np.random.default_rng(n), (n, cols), np.float32)
+    want = comparand.vert(x)
+    bits = n.bit_length() - 1
+    perm = np.array([int(format(i, f"0{bits}b")[::-1], 2) if bits else 0 for i in range(n)])
+    scr = np.empty_like(x)
+    scr[perm] = x  # scramble_rows: out row bitrev(r) = in row r
+    d = torch.from_numpy(scr).cuda()
+    g.FFTVert(n, np.float32).transform_no_scramble(d, cols, cols)
+    assert oracle.rel_l2(d.cpu().numpy(), want) <= oracle.tolerance(n, np.float32)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 2), (4, 8), (8, 4), (64, 32), (16, 1024), (1024, 16), (512, 512),
+                                 (2048, 256), (256, 8192), (32768, 8)])
+def test_fft2d_vs_reference(comparand, dt, w, h):
+    x = rand_cpx(np.random.default_rng(w * 3 + h), (h, w), dt)
+    plan = g.FFT2D(w, h, dt)
+    assert plan.cols() == w and plan.rows() == h
+    for inv in (False, True):
+        want = comparand.fft2d(x, inv)
+        d_out = torch.empty((h, w), dtype=TCPX[dt], device="cuda")
+        plan.transform(d_out, torch.from_numpy(x).cuda(), inv=inv)
+        got = d_out.cpu().numpy()
+        assert oracle.rel_l2(got, want) <= oracle.tolerance(w * h, dt), plan.describe()
+    np_want = np.fft.fft2(x.astype(np.complex128))
+    d_out = torch.empty((h, w), dtype=TCPX[dt], device="cuda")
+    plan.transform(d_out, torch.from_numpy(x).cuda())
+    assert oracle.rel_l2(d_out.cpu().numpy(), np_want) <= oracle.tolerance(w * h, dt)
+
+
+def test_fft2d_strides_and_host(comparand):
+    w, h, in_stride, out_stride = 64, 16, 70, 96
+    buf = rand_cpx(np.random.default_rng(3), (h, in_stride), np.float32)
+    want = comparand.fft2d(np.ascontiguousarray(buf[:, :w]))
+    plan = g.FFT2D(w, h, np.float32)
+    d_out = torch.full((h, out_stride), FILL, dtype=torch.complex64, device="cuda")
+    plan.transform(d_out, torch.from_numpy(buf).cuda(), out_stride=out_stride, in_stride=in_stride)
+    got = d_out.cpu().numpy()
+    assert oracle.rel_l2(got[:, :w], want) <= oracle.tolerance(w * h, np.float32)
+    assert np.all(got[:, w:] == FILL)
+    h_out = np.full((h, out_stride), FILL, dtype=np.complex64)
+    plan.transform(h_out, buf, out_stride=out_stride, in_stride=in_stride)
+    assert oracle.rel_l2(h_out[:, :w], want) <= oracle.tolerance(w * h, np.float32)
+    with pytest.raises(g.GenfftCudaError):
+        plan.transform(h_out, h_out)  # out != in (fft.h:209)
+
+
+def test_c4_real_2pow22_batch_properties(comparand):
+    """BASELINE config C4 (R2C fp32 N=2^22, batch 256) at full size: sampled transforms vs the reference,
+    DC / Nyquist bins are real, and Parseval over the whole batch."""
+    n, batch = 1 << 22, 256
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand((batch, n), generator=gen, device="cuda") * 2 - 1
+    out = torch.empty((batch, n // 2 + 1), dtype=torch.complex64, device="cuda")
+    plan = g.RealFFT(n, np.float32, half=True, batch=batch)
+    plan.forward(out, x)
+    for b in (0, 100, batch - 1):
+        want = comparand.r2c(x[b].cpu().numpy(), True)[: n // 2 + 1]
+        assert oracle.rel_l2(out[b].cpu().numpy(), want) <= oracle.tolerance(n, np.float32), plan.describe()
+    assert out[:, 0].imag.abs().max().item() == 0 and out[:, -1].imag.abs().max().item() == 0
+    ex = (x.double() ** 2).sum(1)
+    p = out.abs().double() ** 2
+    ey = (2 * p.sum(1) - p[:, 0] - p[:, -1]) / n
+    assert ((ey / ex - 1).abs().max().item()) < 1e-5
+
+
+def test_c5_shape_2d_properties():
+    """BASELINE config C5's row/column length (32768) on one GPU at reduced height x full width and
+    full height x reduced width: analytic plane-wave response and round trip."""
+    for w, h in ((32768, 64), (64, 32768)):
+        plan = g.FFT2D(w, h, np.float32)
+        kx, ky = 12345 % w, 17 % h
+        xs = torch.arange(w, device="cuda", dtype=torch.float64)
+        ys = torch.arange(h, device="cuda", dtype=torch.float64)
+        phase = 2 * np.pi * (kx * xs[None, :] / w + ky * ys[:, None] / h)
+        x = torch.polar(torch.ones_like(phase), phase).to(torch.complex64)
+        y = torch.empty_like(x)
+        plan.transform(y, x)
+        peak = y[ky, kx].item()
+        assert abs(peak - w * h) / (w * h) < 1e-4
+        y[ky, kx] = 0
+        assert y.abs().max().item() / (w * h) < 1e-4
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        r = torch.view_as_complex(torch.rand((h, w, 2), generator=gen, device="cuda") * 2 - 1)
+        f = torch.empty_like(r)
+        b = torch.empty_like(r)
+        plan.transform(f, r)
+        plan.transform(b, f, inv=True)
+        assert (b / (w * h) - r).abs().max().item() < 1e-4

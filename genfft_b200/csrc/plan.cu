@@ -194,6 +194,49 @@ static int twiddle_table(int device, int precision, long long M, long long step,
   return GENFFT_CUDA_OK;
 }
 
+// stage twiddles of one kernel configuration (L, P): for every radix stage s >= 1 a block [q][p] of
+// W_{NS*R}^(p*q), q < R, p < NS (see tile_kernel.cuh)
+static std::map<std::tuple<int, int, int, int>, void*> g_stage_tables;
+
+static int stage_twiddle_table(int device, int precision, const KernelEntry* k, const void** out) {
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_tuple(device, precision, k->L, k->P);
+  auto it = g_stage_tables.find(key);
+  if (it != g_stage_tables.end()) {
+    *out = it->second;
+    return GENFFT_CUDA_OK;
+  }
+  const int L = k->L, P = k->P;
+  const int nst = num_stages(L, P);
+  const size_t count = (size_t)std::max(1, stage_tw_size(L, P));
+  const size_t es = elem_size(precision);
+  std::vector<unsigned char> host(es * count, 0);
+  for (int s = 1; s < nst; s++) {
+    const int R = stage_radix(L, P, s), NS = stage_ns(L, P, s), off = stage_tw_offset(L, P, s);
+    for (int q = 0; q < R; q++)
+      for (int p = 0; p < NS; p++) {
+        long double c, sn;
+        unit_root((unsigned long long)p * q, (unsigned long long)NS * R, &c, &sn);
+        const size_t e = (size_t)off + (size_t)q * NS + p;
+        if (precision == GENFFT_CUDA_F32) {
+          float* t = reinterpret_cast<float*>(host.data()) + 2 * e;
+          t[0] = (float)c;
+          t[1] = (float)-sn;
+        } else {
+          double* t = reinterpret_cast<double*>(host.data()) + 2 * e;
+          t[0] = (double)c;
+          t[1] = (double)-sn;
+        }
+      }
+  }
+  void* d = nullptr;
+  CU_TRY(cudaMalloc(&d, host.size()));
+  CU_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+  g_stage_tables[key] = d;
+  *out = d;
+  return GENFFT_CUDA_OK;
+}
+
 // two-level table for W_M^e, e < M: W = hi[e >> shift] * lo[e & (2^shift - 1)]
 static int two_level_table(int device, int precision, long long M, const void** hi, const void** lo, int* shift) {
   const int lg = ilog2(M);
@@ -248,7 +291,7 @@ static int build_seq(Seq* seq, int device, int precision, long long N, bool wide
     int occ;
     int rc = kernel_occupancy(ps.k, device, &occ);
     if (rc) return rc;
-    rc = twiddle_table(device, precision, ps.R, 1, ps.R, &ps.tw_L);
+    rc = stage_twiddle_table(device, precision, ps.k, &ps.tw_L);
     if (rc) return rc;
     if (Ns > 1) {
       rc = two_level_table(device, precision, Ns * ps.R, &ps.tw_hi, &ps.tw_lo, &ps.tw_shift);

@@ -52,7 +52,8 @@ struct PassParams {
   int tw_shift;     // e = p*idx ; W = tw_hi[e >> tw_shift] * tw_lo[e & ((1<<tw_shift)-1)]
   int p_t1, p_c;
   uint32_t p_mask;  // p &= p_mask
-  // on-chip stage twiddles W_L^e, e < L
+  // on-chip stage twiddles, one block per radix stage s >= 1 laid out [q][p]:
+  //   tw_L[stage_tw_offset(s) + q*NS + p] = W_{NS*R}^(p*q)   (lanes read consecutive p: coalesced)
   const void* tw_L;
 };
 
@@ -71,6 +72,14 @@ __host__ __device__ constexpr int stage_ns(int L, int P, int s) {
   for (int k = 0; k < s; k++) ns *= stage_radix(L, P, k);
   return ns;
 }
+
+// offset of stage s's block in the stage-twiddle table (stage 0 needs none)
+__host__ __device__ constexpr int stage_tw_offset(int L, int P, int s) {
+  int off = 0;
+  for (int k = 1; k < s; k++) off += stage_ns(L, P, k) * stage_radix(L, P, k);
+  return off;
+}
+__host__ __device__ constexpr int stage_tw_size(int L, int P) { return stage_tw_offset(L, P, num_stages(L, P)); }
 
 // one padding element per 16: conflict-free for the stride-r scatters of every radix <= 16
 __host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 4); }
@@ -196,7 +205,7 @@ struct TileKernel {
       if (NS > 1) {
 #pragma unroll
         for (int q = 1; q < R; q++) {
-          V w = __ldg(twL + (p * q) * (L / (NS * R)));
+          V w = __ldg(twL + (stage_tw_offset(L, P, S) + q * NS + p));
           y[q] = cmul(y[q], cpx<T>(w.x, w.y));
         }
       }
@@ -263,8 +272,16 @@ struct TileKernel {
   }
 };
 
+// resident-thread target per SM: 1024 (64 registers) in float, 512 (128 registers) in double, where a
+// thread's 16 complex points alone are 64 registers
+template <typename T, int THREADS>
+constexpr int min_blocks() {
+  constexpr int target = sizeof(T) == 4 ? 1024 : 512;
+  return THREADS >= target ? 1 : target / THREADS;
+}
+
 template <typename T, int L, int P, int C>
-__global__ void __launch_bounds__(TileKernel<T, L, P, C>::THREADS)
+__global__ void __launch_bounds__(TileKernel<T, L, P, C>::THREADS, min_blocks<T, TileKernel<T, L, P, C>::THREADS>())
 fft_tile_kernel(const __grid_constant__ PassParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileKernel<T, L, P, C>::body(prm, reinterpret_cast<cpx<T>*>(smem_raw));

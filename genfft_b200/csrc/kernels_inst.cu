@@ -8,61 +8,64 @@
 
 namespace genfft_cuda {
 
-#define ADD(T, L, P, C) v.push_back(make_entry<T, L, P, C>())
+// N: narrow only, W: wide only, B: used both ways
+#define ADD_N(T, L, P, C) v.push_back(make_entry<T, L, P, C, true, false>())
+#define ADD_W(T, L, P, C) v.push_back(make_entry<T, L, P, C, false, true>())
+#define ADD_B(T, L, P, C) v.push_back(make_entry<T, L, P, C, true, true>())
 
 #if GENFFT_KSET == 0
 void register_kernels_f32_small(std::vector<KernelEntry>& v) {
-  ADD(float, 2, 2, 128);
-  ADD(float, 4, 4, 128);
-  ADD(float, 8, 8, 128);
-  ADD(float, 16, 16, 128);
-  ADD(float, 32, 16, 64);
-  ADD(float, 64, 16, 32);
-  ADD(float, 128, 16, 16);
-  ADD(float, 256, 16, 16);
+  ADD_B(float, 2, 2, 128);
+  ADD_B(float, 4, 4, 128);
+  ADD_B(float, 8, 8, 128);
+  ADD_B(float, 16, 16, 128);
+  ADD_B(float, 32, 16, 64);
+  ADD_B(float, 64, 16, 32);
+  ADD_B(float, 128, 16, 16);
+  ADD_B(float, 256, 16, 16);
 }
 #elif GENFFT_KSET == 1
 void register_kernels_f32_mid(std::vector<KernelEntry>& v) {
-  ADD(float, 512, 16, 8);
-  ADD(float, 512, 16, 16);
-  ADD(float, 1024, 16, 4);
-  ADD(float, 1024, 16, 16);
-  ADD(float, 2048, 16, 2);
-  ADD(float, 2048, 16, 8);
+  ADD_N(float, 512, 16, 8);
+  ADD_W(float, 512, 16, 16);
+  ADD_N(float, 1024, 16, 4);
+  ADD_W(float, 1024, 16, 16);
+  ADD_N(float, 2048, 16, 2);
+  ADD_W(float, 2048, 16, 8);
 }
 #elif GENFFT_KSET == 2
 void register_kernels_f32_large(std::vector<KernelEntry>& v) {
-  ADD(float, 4096, 16, 1);
-  ADD(float, 4096, 16, 4);
-  ADD(float, 8192, 16, 1);
-  ADD(float, 8192, 16, 2);
-  ADD(float, 16384, 16, 1);
+  ADD_N(float, 4096, 16, 1);
+  ADD_W(float, 4096, 16, 4);
+  ADD_N(float, 8192, 16, 1);
+  ADD_W(float, 8192, 16, 2);
+  ADD_B(float, 16384, 16, 1);
 }
 #elif GENFFT_KSET == 3
 void register_kernels_f64_small(std::vector<KernelEntry>& v) {
-  ADD(double, 2, 2, 128);
-  ADD(double, 4, 4, 128);
-  ADD(double, 8, 8, 128);
-  ADD(double, 16, 16, 128);
-  ADD(double, 32, 16, 64);
-  ADD(double, 64, 16, 32);
-  ADD(double, 128, 16, 16);
-  ADD(double, 256, 16, 8);
-  ADD(double, 256, 16, 16);
+  ADD_B(double, 2, 2, 128);
+  ADD_B(double, 4, 4, 128);
+  ADD_B(double, 8, 8, 128);
+  ADD_B(double, 16, 16, 128);
+  ADD_B(double, 32, 16, 64);
+  ADD_B(double, 64, 16, 32);
+  ADD_B(double, 128, 16, 16);
+  ADD_N(double, 256, 16, 8);
+  ADD_W(double, 256, 16, 16);
 }
 #elif GENFFT_KSET == 4
 void register_kernels_f64_mid(std::vector<KernelEntry>& v) {
-  ADD(double, 512, 16, 8);
-  ADD(double, 1024, 16, 4);
-  ADD(double, 1024, 16, 8);
-  ADD(double, 2048, 16, 2);
-  ADD(double, 2048, 16, 4);
+  ADD_B(double, 512, 16, 8);
+  ADD_N(double, 1024, 16, 4);
+  ADD_W(double, 1024, 16, 8);
+  ADD_N(double, 2048, 16, 2);
+  ADD_W(double, 2048, 16, 4);
 }
 #elif GENFFT_KSET == 5
 void register_kernels_f64_large(std::vector<KernelEntry>& v) {
-  ADD(double, 4096, 16, 1);
-  ADD(double, 4096, 16, 2);
-  ADD(double, 8192, 16, 1);
+  ADD_N(double, 4096, 16, 1);
+  ADD_W(double, 4096, 16, 2);
+  ADD_B(double, 8192, 16, 1);
 }
 #else
 #error "GENFFT_KSET must be 0..5"

@@ -111,18 +111,18 @@ static const KernelEntry* find_kernel(int precision, long long L, bool wide) {
 static std::mutex g_cfg_mu;
 static std::map<std::pair<int, const void*>, int> g_occupancy;  // (device, func) -> CTAs per SM
 
-static int kernel_occupancy(const KernelEntry* k, int device, int* out) {
+static int kernel_occupancy(const KernelEntry* k, const void* func, int device, int* out) {
   std::lock_guard<std::mutex> lk(g_cfg_mu);
-  auto key = std::make_pair(device, k->func);
+  auto key = std::make_pair(device, func);
   auto it = g_occupancy.find(key);
   if (it != g_occupancy.end()) {
     *out = it->second;
     return GENFFT_CUDA_OK;
   }
   if (k->smem > 48 * 1024)
-    CU_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    CU_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
   int n = 0;
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k->func, k->threads, k->smem));
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, func, k->threads, k->smem));
   if (n < 1) return fail(GENFFT_CUDA_ERR_CUDA, "kernel L=%d C=%d cannot be resident (smem %zu)", k->L, k->C, k->smem);
   g_occupancy[key] = n;
   *out = n;
@@ -288,10 +288,7 @@ static int build_seq(Seq* seq, int device, int precision, long long N, bool wide
     ps.Ns = Ns;
     ps.k = find_kernel(precision, ps.R, wide || multi);
     if (!ps.k) return fail(GENFFT_CUDA_ERR_SIZE, "no kernel for pass length %lld", ps.R);
-    int occ;
-    int rc = kernel_occupancy(ps.k, device, &occ);
-    if (rc) return rc;
-    rc = stage_twiddle_table(device, precision, ps.k, &ps.tw_L);
+    int rc = stage_twiddle_table(device, precision, ps.k, &ps.tw_L);
     if (rc) return rc;
     if (Ns > 1) {
       rc = two_level_table(device, precision, Ns * ps.R, &ps.tw_hi, &ps.tw_lo, &ps.tw_shift);
@@ -340,10 +337,12 @@ static PassParams emit_1d(const PassSpec& ps, long long N, const void* in, long 
     p.out_stride_k = 1;
     p.out_stride_c = out_dist;
     p.map_load = p.map_store = 1;
+    p.mode = M_ROW;
     if (brev) {
       p.brev_bits = ilog2(N);
       p.g_i = 1;
       p.brev_stride = 1;
+      p.mode = M_GEN;
     }
   } else if (Ns == 1) {  // first pass: y[j*R + k] = DFT_R over i of x[j + i*N/R]
     const long long cols = N / R;
@@ -358,12 +357,14 @@ static PassParams emit_1d(const PassSpec& ps, long long N, const void* in, long 
     p.out_stride_c = R;
     p.map_load = 0;
     p.map_store = 1;
+    p.mode = M_FIRST;
     if (brev) {
       p.brev_bits = ilog2(N);
       p.g_c = 1;
       p.g_i = cols;
       p.brev_stride = 1;
       p.in_stride_c = 0;
+      p.mode = M_GEN;
     }
   } else {  // later pass: j = a*Ns + p;  y[a*Ns*R + p + k*Ns] = DFT_R over i of W^(p*i) x[j + i*N/R]
     const long long a_cnt = N / (R * Ns);
@@ -382,6 +383,7 @@ static PassParams emit_1d(const PassSpec& ps, long long N, const void* in, long 
     p.map_load = p.map_store = 0;
     p.p_c = 1;
     p.p_mask = (uint32_t)(Ns - 1);
+    p.mode = M_COLTW;
   }
   return p;
 }
@@ -397,6 +399,8 @@ static PassParams emit_col(const PassSpec& ps, long long N, const void* in, long
   p.in_stride_c = 1;
   p.out_stride_c = 1;
   p.map_load = p.map_store = 0;
+  p.mode = (Ns == 1) ? M_COL : M_COLTW;
+  if (brev) p.mode = M_GEN;
   if (N == R) {
     p.ntiles = p.n2;
     p.in_stride_i = in_pitch;
@@ -437,12 +441,15 @@ static PassParams emit_col(const PassSpec& ps, long long N, const void* in, long
 
 static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p, cudaStream_t stream) {
   if (p.ntiles == 0) return GENFFT_CUDA_OK;
+  int mode = p.mode;
+  const int inv = p.inverse ? 1 : 0;
+  if (mode < 0 || mode >= kNumModes || !ps.k->launch[mode][inv]) mode = M_GEN;
   int occ = 1;
-  int rc = kernel_occupancy(ps.k, plan->device, &occ);
+  int rc = kernel_occupancy(ps.k, ps.k->func[mode][inv], plan->device, &occ);
   if (rc) return rc;
   long long cap = (long long)plan->num_sms * occ;
   int grid = (int)std::min<long long>(p.ntiles, cap);
-  ps.k->launch(p, grid, stream);
+  ps.k->launch[mode][inv](p, grid, stream);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
@@ -607,8 +614,12 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     }
     PassParams p = st.col ? emit_col(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, cols, inverse, st.brev)
                           : emit_1d(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, count, inverse, st.brev);
-    if (st.real_in) p.in_real = 1;
+    if (st.real_in) {
+      p.in_real = 1;
+      p.mode = M_GEN;
+    }
     if (fs && s == n - 1) {
+      p.mode = M_GEN;
       const long long Ns = (st.N == st.ps->R) ? 1 : st.ps->Ns;
       const int sh = fs->part_log2 - ilog2(Ns);
       if (sh < 0) return fail(GENFFT_CUDA_ERR_SIZE, "part size 2^%d smaller than pass stride %lld", fs->part_log2, Ns);

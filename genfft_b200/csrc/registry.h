@@ -6,37 +6,58 @@
 
 namespace genfft_cuda {
 
+constexpr int kNumModes = 5;
+
 struct KernelEntry {
   int L, P, C;
   int threads;
   size_t smem;
-  const void* func;  // __global__ function pointer (for attributes / occupancy)
-  void (*launch)(const PassParams& prm, int grid, cudaStream_t stream);
-  int max_ctas_per_sm;  // filled lazily per device
+  // [mode][inverse]; null when that variant is not compiled for this shape (M_GEN always is, with
+  // the direction taken at run time, stored in both slots)
+  const void* func[kNumModes][2];
+  void (*launch[kNumModes][2])(const PassParams& prm, int grid, cudaStream_t stream);
 };
 
-template <typename T, int L, int P, int C>
+template <typename T, int L, int P, int C, int MODE, bool INV>
 void launch_tile(const PassParams& prm, int grid, cudaStream_t stream) {
-  using K = TileKernel<T, L, P, C>;
-  fft_tile_kernel<T, L, P, C><<<grid, K::THREADS, K::SMEM_BYTES, stream>>>(prm);
+  using K = TileKernel<T, L, P, C, MODE, INV>;
+  fft_tile_kernel<T, L, P, C, MODE, INV><<<grid, K::THREADS, K::SMEM_BYTES, stream>>>(prm);
 }
 
-template <typename T, int L, int P, int C>
+template <typename T, int L, int P, int C, int MODE>
+void add_mode(KernelEntry& e) {
+  e.func[MODE][0] = reinterpret_cast<const void*>(&fft_tile_kernel<T, L, P, C, MODE, false>);
+  e.launch[MODE][0] = &launch_tile<T, L, P, C, MODE, false>;
+  if (MODE == M_GEN) {
+    e.func[MODE][1] = e.func[MODE][0];
+    e.launch[MODE][1] = e.launch[MODE][0];
+  } else {
+    e.func[MODE][1] = reinterpret_cast<const void*>(&fft_tile_kernel<T, L, P, C, MODE, MODE != M_GEN>);
+    e.launch[MODE][1] = &launch_tile<T, L, P, C, MODE, MODE != M_GEN>;
+  }
+}
+
+// narrow: contiguous batched use; wide: column / multi-pass use
+template <typename T, int L, int P, int C, bool NARROW, bool WIDE>
 KernelEntry make_entry() {
-  using K = TileKernel<T, L, P, C>;
-  KernelEntry e;
+  using K = TileKernel<T, L, P, C, M_GEN, false>;
+  KernelEntry e = {};
   e.L = L;
   e.P = P;
   e.C = C;
   e.threads = K::THREADS;
   e.smem = K::SMEM_BYTES;
-  e.func = reinterpret_cast<const void*>(&fft_tile_kernel<T, L, P, C>);
-  e.launch = &launch_tile<T, L, P, C>;
-  e.max_ctas_per_sm = 0;
+  add_mode<T, L, P, C, M_GEN>(e);
+  if constexpr (NARROW) add_mode<T, L, P, C, M_ROW>(e);
+  if constexpr (WIDE) {
+    add_mode<T, L, P, C, M_COL>(e);
+    add_mode<T, L, P, C, M_COLTW>(e);
+    add_mode<T, L, P, C, M_FIRST>(e);
+  }
   return e;
 }
 
-// defined in kernels_*.cu
+// defined in kernels_inst.cu (compiled once per GENFFT_KSET)
 void register_kernels_f32_small(std::vector<KernelEntry>& v);
 void register_kernels_f32_mid(std::vector<KernelEntry>& v);
 void register_kernels_f32_large(std::vector<KernelEntry>& v);

@@ -40,6 +40,7 @@ struct PassParams {
   int use_peers;             // 1: (k >> out_split_log2) selects out_peer[], out_stride_khi ignored
   int ncols;                 // valid columns along t2*C + c (tail tiles are masked)
   int map_load, map_store;   // 0 = lanes across columns (A), 1 = lanes along the sequence (B)
+  int mode;                  // host side only: which compiled addressing mode to launch (enum Mode)
   int inverse;               // conjugate on load and on store
   int in_real;               // input is real scalars (imag = 0); FFT<T>::transform_real, fft.h:90-94
   // bit-reversed input (transform_no_scramble contract, fft.h:69-73 / 132-136):
@@ -85,13 +86,26 @@ __host__ __device__ constexpr int stage_tw_size(int L, int P) { return stage_tw_
 __host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 4); }
 __host__ __device__ constexpr int tile_pitch(int L) { return pad_idx(L) | 1; }
 
-template <typename T, int L, int P, int C>
+// Addressing modes.  M_GEN handles everything at run time (bit-reversed / real input, split and peer
+// stores, any mapping); the others are the hot paths with the addressing resolved at compile time so
+// that global and shared accesses use immediate offsets from one base register and the direction
+// (INV: conjugate on load and store) folds into the butterflies' operand negations.
+//   M_ROW   : unit stride in and out, lanes along the sequence        (batched contiguous 1D, 2D rows)
+//   M_COL   : strided in and out, lanes across columns                (FFTVert, 2D columns, last pass)
+//   M_COLTW : M_COL + inter-pass Stockham twiddle fused into the load (later passes of a large N)
+//   M_FIRST : strided in (lanes across columns), unit-stride out      (first pass of a large N)
+enum Mode { M_GEN = 0, M_ROW = 1, M_COL = 2, M_COLTW = 3, M_FIRST = 4 };
+
+template <typename T, int L, int P, int C, int MODE, bool INV>
 struct TileKernel {
   static constexpr int TN = L / P;
   static constexpr int THREADS = TN * C;
   static constexpr int NST = num_stages(L, P);
   static constexpr int PITCH = tile_pitch(L);
   static constexpr size_t SMEM_BYTES = NST > 1 ? sizeof(cpx<T>) * (size_t)PITCH * C : 0;
+  static constexpr bool GEN = MODE == M_GEN;
+  static constexpr bool UNIT_IN = MODE == M_ROW;
+  static constexpr bool UNIT_OUT = MODE == M_ROW || MODE == M_FIRST;
   using V = typename vec2<T>::type;
 
   static __device__ __forceinline__ uint32_t brev(uint32_t v, int bits) { return __brev(v) >> (32 - bits); }
@@ -104,24 +118,74 @@ struct TileKernel {
   };
 
   static __device__ __forceinline__ Tile decode(const PassParams& prm, uint32_t tile) {
+    Tile t;
+    if constexpr (MODE == M_ROW) {  // columns are whole transforms; no outer tile indices
+      t.col0 = tile * C;
+      t.in_off = t.out_off = 0;
+      t.p_base = 0;
+      t.g_base = 0;
+    } else {
     uint32_t t2 = tile % prm.n2;
     uint32_t t01 = tile / prm.n2;
     uint32_t t1 = t01 % prm.n1;
     uint32_t t0 = t01 / prm.n1;
-    Tile t;
     t.col0 = t2 * C;
     t.in_off = (long long)t0 * prm.in_t0 + (long long)t1 * prm.in_t1;
     t.out_off = (long long)t0 * prm.out_t0 + (long long)t1 * prm.out_t1;
     t.p_base = t1 * (uint32_t)prm.p_t1;
     t.g_base = (long long)t1 * prm.g_t1;
-    if (prm.brev_bits) t.in_off = (long long)t0 * prm.in_t0;
+    if (GEN && prm.brev_bits) t.in_off = (long long)t0 * prm.in_t0;
+    }
     return t;
+  }
+
+  static __device__ __forceinline__ bool is_inverse(const PassParams& prm) { return GEN ? prm.inverse != 0 : INV; }
+
+  static __device__ __forceinline__ void apply_pass_twiddle(const PassParams& prm, const Tile& t, uint32_t col, int u,
+                                                            cpx<T> (&x)[P]) {
+    const uint32_t p = (t.p_base + col * (uint32_t)prm.p_c) & prm.p_mask;
+    const V* hi = reinterpret_cast<const V*>(prm.tw_hi);
+    const V* lo = reinterpret_cast<const V*>(prm.tw_lo);
+    const uint32_t lomask = (1u << prm.tw_shift) - 1u;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const uint32_t e = p * (uint32_t)(u + i * TN);
+      V a = __ldg(hi + (e >> prm.tw_shift));
+      V b = __ldg(lo + (e & lomask));
+      cpx<T> w = cmul(cpx<T>(a.x, a.y), cpx<T>(b.x, b.y));
+      x[i] = cmul(x[i], w);
+    }
   }
 
   static __device__ __forceinline__ void load(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {
     const uint32_t col = t.col0 + c;
     const bool valid = col < (uint32_t)prm.ncols;
     const long long base = t.in_off + (long long)col * prm.in_stride_c;
+    if constexpr (!GEN) {
+      if (valid) {
+        if constexpr (UNIT_IN) {
+          const V* src = reinterpret_cast<const V*>(prm.in) + base + u;
+#pragma unroll
+          for (int i = 0; i < P; i++) {
+            V v = src[i * TN];
+            x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
+          }
+        } else {
+          const V* src = reinterpret_cast<const V*>(prm.in) + base + (long long)u * prm.in_stride_i;
+          const long long step = (long long)TN * prm.in_stride_i;
+#pragma unroll
+          for (int i = 0; i < P; i++) {
+            V v = *src;
+            src += step;
+            x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < P; i++) x[i] = cpx<T>(T(0), T(0));
+      }
+      if constexpr (MODE == M_COLTW) apply_pass_twiddle(prm, t, col, u, x);
+    } else {
 #pragma unroll
     for (int i = 0; i < P; i++) {
       const int idx = u + i * TN;
@@ -147,19 +211,7 @@ struct TileKernel {
 #pragma unroll
       for (int i = 0; i < P; i++) x[i].y = -x[i].y;
     }
-    if (prm.tw_hi) {
-      const uint32_t p = (t.p_base + col * (uint32_t)prm.p_c) & prm.p_mask;
-      const V* hi = reinterpret_cast<const V*>(prm.tw_hi);
-      const V* lo = reinterpret_cast<const V*>(prm.tw_lo);
-      const uint32_t lomask = (1u << prm.tw_shift) - 1u;
-#pragma unroll
-      for (int i = 0; i < P; i++) {
-        const uint32_t e = p * (uint32_t)(u + i * TN);
-        V a = __ldg(hi + (e >> prm.tw_shift));
-        V b = __ldg(lo + (e & lomask));
-        cpx<T> w = cmul(cpx<T>(a.x, a.y), cpx<T>(b.x, b.y));
-        x[i] = cmul(x[i], w);
-      }
+    if (prm.tw_hi) apply_pass_twiddle(prm, t, col, u, x);
     }
   }
 
@@ -167,6 +219,29 @@ struct TileKernel {
     const uint32_t col = t.col0 + c;
     if (col >= (uint32_t)prm.ncols) return;
     const long long base = t.out_off + (long long)col * prm.out_stride_c;
+    if constexpr (!GEN) {
+      if constexpr (UNIT_OUT) {
+        V* dst = reinterpret_cast<V*>(prm.out) + base + u;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+          V v;
+          v.x = x[i].x;
+          v.y = INV ? -x[i].y : x[i].y;
+          dst[i * TN] = v;
+        }
+      } else {
+        V* dst = reinterpret_cast<V*>(prm.out) + base + (long long)u * prm.out_stride_k;
+        const long long step = (long long)TN * prm.out_stride_k;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+          V v;
+          v.x = x[i].x;
+          v.y = INV ? -x[i].y : x[i].y;
+          *dst = v;
+          dst += step;
+        }
+      }
+    } else {
 #pragma unroll
     for (int i = 0; i < P; i++) {
       const int k = u + i * TN;
@@ -184,6 +259,7 @@ struct TileKernel {
           reinterpret_cast<V*>(prm.out)[base + (long long)klo * prm.out_stride_k + (long long)khi * prm.out_stride_khi] = v;
         }
       }
+    }
     }
   }
 
@@ -203,9 +279,10 @@ struct TileKernel {
 #pragma unroll
       for (int q = 0; q < R; q++) y[q] = x[m + q * M];
       if (NS > 1) {
+        const V* tw = twL + (stage_tw_offset(L, P, S) + p);
 #pragma unroll
         for (int q = 1; q < R; q++) {
-          V w = __ldg(twL + (stage_tw_offset(L, P, S) + q * NS + p));
+          V w = __ldg(tw + q * NS);
           y[q] = cmul(y[q], cpx<T>(w.x, w.y));
         }
       }
@@ -216,23 +293,45 @@ struct TileKernel {
         for (int s = 0; s < R; s++) x[m + RegDFT<R>::out_bin(s) * M] = y[s];
       } else {
         const int base = (j - p) * R + p;
+        if constexpr (NS >= 16 || NS == 1) {
+          // pad_idx(base + b*NS) == pad_idx(base) + b*(NS + NS/16): immediate offsets from one address
+          V* dst = reinterpret_cast<V*>(sm) + pad_idx(base);
 #pragma unroll
-        for (int s = 0; s < R; s++) {
-          const int pos = base + RegDFT<R>::out_bin(s) * NS;
-          V v;
-          v.x = y[s].x;
-          v.y = y[s].y;
-          reinterpret_cast<V*>(sm)[pad_idx(pos)] = v;
+          for (int s = 0; s < R; s++) {
+            const int b = RegDFT<R>::out_bin(s);
+            V v;
+            v.x = y[s].x;
+            v.y = y[s].y;
+            dst[NS == 1 ? b : b * (NS + NS / 16)] = v;
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < R; s++) {
+            const int pos = base + RegDFT<R>::out_bin(s) * NS;
+            V v;
+            v.x = y[s].x;
+            v.y = y[s].y;
+            reinterpret_cast<V*>(sm)[pad_idx(pos)] = v;
+          }
         }
       }
     }
   }
 
   static __device__ __forceinline__ void gather(cpx<T> (&x)[P], const cpx<T>* sm, int u) {
+    if constexpr (TN >= 16) {
+      const V* src = reinterpret_cast<const V*>(sm) + pad_idx(u);
 #pragma unroll
-    for (int i = 0; i < P; i++) {
-      V v = reinterpret_cast<const V*>(sm)[pad_idx(u + i * TN)];
-      x[i] = cpx<T>(v.x, v.y);
+      for (int i = 0; i < P; i++) {
+        V v = src[i * (TN + TN / 16)];
+        x[i] = cpx<T>(v.x, v.y);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        V v = reinterpret_cast<const V*>(sm)[pad_idx(u + i * TN)];
+        x[i] = cpx<T>(v.x, v.y);
+      }
     }
   }
 
@@ -256,10 +355,12 @@ struct TileKernel {
 
   static __device__ __forceinline__ void body(const PassParams& prm, cpx<T>* smem) {
     const int tid = threadIdx.x;
-    const int c_ld = prm.map_load ? tid / TN : tid % C;
-    const int u_ld = prm.map_load ? tid % TN : tid / C;
-    const int c_st = prm.map_store ? tid / TN : tid % C;
-    const int u_st = prm.map_store ? tid % TN : tid / C;
+    const bool ld_b = GEN ? prm.map_load != 0 : MODE == M_ROW;
+    const bool st_b = GEN ? prm.map_store != 0 : (MODE == M_ROW || MODE == M_FIRST);
+    const int c_ld = ld_b ? tid / TN : tid % C;
+    const int u_ld = ld_b ? tid % TN : tid / C;
+    const int c_st = st_b ? tid / TN : tid % C;
+    const int u_st = st_b ? tid % TN : tid / C;
     cpx<T> x[P];
     for (uint32_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
       Tile t = decode(prm, tile);
@@ -280,11 +381,12 @@ constexpr int min_blocks() {
   return THREADS >= target ? 1 : target / THREADS;
 }
 
-template <typename T, int L, int P, int C>
-__global__ void __launch_bounds__(TileKernel<T, L, P, C>::THREADS, min_blocks<T, TileKernel<T, L, P, C>::THREADS>())
+template <typename T, int L, int P, int C, int MODE, bool INV>
+__global__ void __launch_bounds__(TileKernel<T, L, P, C, MODE, INV>::THREADS,
+                                  min_blocks<T, TileKernel<T, L, P, C, MODE, INV>::THREADS>())
 fft_tile_kernel(const __grid_constant__ PassParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileKernel<T, L, P, C>::body(prm, reinterpret_cast<cpx<T>*>(smem_raw));
+  TileKernel<T, L, P, C, MODE, INV>::body(prm, reinterpret_cast<cpx<T>*>(smem_raw));
 }
 
 }  // namespace genfft_cuda

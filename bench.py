@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the transform hot path (contract: one JSON line on stdout from rank 0).
+
+Workload at every N: BASELINE.json configs[1] ("C2") -- batched 1D complex fp32 C2C, N = 4096 x 2^16
+forward transforms per GPU (a "step" = one pass of the hot path over that batch).  With N > 1 GPUs the
+batch is sharded: every rank transforms its own 2^16 sequences, no collective on the data path
+("scaling": "weak"), value = transforms of all ranks / max-over-ranks device time.
+
+  value      effective GFLOP/s = 5 N log2 N * batch / t, inputs resident in HBM, CUDA events
+  roofline   algorithmic bytes (one read + one write of the batch) / kernel time vs measured HBM peak
+  e2e        same metric through the host-pointer C-ABI call (genfft_cuda_exec_c2c) on pinned host
+             buffers: H2D + kernels + D2H inside the timed region
+  cpu_baseline / --impl reference
+             genFFT's own CPU implementation (oracle/_ref, dispatch AVX2/FMA build) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FFT = 4096
+BATCH = 1 << 16
+METRIC = "effective GFLOP/s (5N*log2N/t), batched 1D C2C fp32 N=4096 x 2^16 per GPU"
+UNIT = "GFLOP/s"
+FLOP_PER_STEP = 5.0 * N_FFT * math.log2(N_FFT) * BATCH
+ALGO_BYTES_PER_STEP = 2 * N_FFT * BATCH * 8  # one read + one write of the batch
+
+
+def config(n_gpus: int) -> dict:
+    return {
+        "workload": "C2: batched 1D C2C fp32 forward, N=4096 x 2^16 transforms per GPU (BASELINE.json configs[1])",
+        "n_fft": N_FFT,
+        "batch_per_gpu": BATCH,
+        "global_batch": BATCH * n_gpus,
+        "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
+        "l2": "inputs (2 GiB per GPU) larger than L2 (126 MB); no flush needed",
+    }
+
+
+def measured_peaks() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args, rank: int, world: int) -> int:
+    """genFFT's own CPU implementation of the path on the host cores (oracle/_ref), same metric/config."""
+    if rank != 0:
+        return 0
+    import oracle
+    if not oracle.have_ref():
+        if os.path.isdir(oracle.REFERENCE_ROOT):
+            oracle.build("ref")
+    if not oracle.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgenfft_ref.so was not built"}))
+        return 0
+    ref = oracle.Ref()
+    threads = ref.hardware_threads()
+    # bounded sample per step: calibrate ~1.5 s of wall per step
+    t_cal = ref.bench_c2c(N_FFT, 64 * threads, threads)
+    per_step = max(threads, int(64 * threads * 1.5 / max(t_cal, 1e-6)))
+    per_step = min(per_step, BATCH * world)
+    for _ in range(args.warmup):
+        ref.bench_c2c(N_FFT, per_step, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += ref.bench_c2c(N_FFT, per_step, threads)
+    ms = 1e3 * t / args.steps
+    value = 5.0 * N_FFT * math.log2(N_FFT) * per_step / (t / args.steps) / 1e9
+    sample = f"{per_step} of {BATCH * world} transforms per step, {threads} host threads, fft_bench.cpp FFT_1D loop (forward only)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic U(-1,1), std::mt19937_64 per thread", "config": config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_build": ref.describe(),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import genfft_b200 as g
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: genfft_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    plan = g.FFT(N_FFT, np.float32, batch=BATCH)
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x = torch.view_as_complex(torch.rand((BATCH, N_FFT, 2), generator=gen, device="cuda") * 2 - 1)
+    y = torch.empty_like(x)
+
+    for _ in range(args.warmup):
+        plan.forward(y, x)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = g.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        plan.forward(y, x)
+        ev[i + 1].record()
+    barrier()
+    launches = g.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = FLOP_PER_STEP * world / (ms_per_step * 1e-3) / 1e9
+
+    # sanity: the timed output is a transform of the input (Parseval), so no work was skipped
+    ex = float((x[:64].abs().double() ** 2).sum())
+    ey = float((y[:64].abs().double() ** 2).sum())
+    assert abs(ey / (N_FFT * ex) - 1) < 1e-4, "output of the timed region is not the transform of the input"
+
+    # ---- e2e: host-pointer C-ABI call on pinned host buffers, H2D + D2H inside the timed region ----
+    hx = torch.empty((BATCH, N_FFT), dtype=torch.complex64, pin_memory=True)
+    hy = torch.empty((BATCH, N_FFT), dtype=torch.complex64, pin_memory=True)
+    hx.copy_(x)
+    plan.forward(hy, hx)  # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        plan.forward(hy, hx)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = FLOP_PER_STEP * world / e2e_s / 1e9
+    err = float((hy[:8].cuda() - y[:8]).abs().max())
+    assert err < 1e-3, f"host-pointer path disagrees with the device path ({err})"
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    kernel_ms = sum(per_kernel_ms) / len(per_kernel_ms)
+    achieved = ALGO_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "c2_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic U(-1,1) generated on device, seeded per rank", "config": config(world),
+        "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_FFT * BATCH * 8,
+                "d2h_bytes_per_step": N_FFT * BATCH * 8, "ms_per_step": e2e_s * 1e3,
+                "api": "genfft_cuda_exec_c2c (host pointers, pinned; chunked H2D/compute/D2H overlap on two streams)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "fft_tile_kernel<float,4096,16,1,M_ROW,false>",
+                     "kernel_ms": kernel_ms, "algorithmic_bytes": ALGO_BYTES_PER_STEP, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "plan": plan.describe(),
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
+    if world == 1:
+        try:
+            import oracle
+            ref = oracle.Ref()
+            threads = ref.hardware_threads()
+            t_cal = ref.bench_c2c(N_FFT, 32 * threads, threads)
+            count = max(threads, int(32 * threads * 10.0 / max(t_cal, 1e-6)))
+            t_cpu = ref.bench_c2c(N_FFT, count, threads)
+            t_one = ref.bench_c2c(N_FFT, 2048, 1)
+            line["cpu_baseline"] = {
+                "value": 5.0 * N_FFT * 12 * count / t_cpu / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": f"{count} of {BATCH} transforms, fresh U(-1,1) input per transform, {threads} threads "
+                          f"(restated fft_bench.cpp FFT_1D loop, forward only); {ref.describe()}",
+                "single_core_value": 5.0 * N_FFT * 12 * 2048 / t_one / 1e9,
+            }
+        except Exception as e:  # the oracle is a checker; its absence must not hide the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": f"unavailable: {e}"}
+        if not args.no_extras:
+            line["extras"] = extras(g, np, torch)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def extras(g, np, torch) -> dict:
+    """Secondary single-GPU configs of BASELINE.json (reported, not the contract metric)."""
+    out = {}
+
+    def timed(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / iters
+
+    peak, _ = measured_peaks()
+    try:
+        # C1: single N=1024 fp32 forward+inverse (latency)
+        p = g.FFT(1024, np.float32)
+        x = torch.randn(1024, dtype=torch.complex64, device="cuda")
+        y, z = torch.empty_like(x), torch.empty_like(x)
+        ms = timed(lambda: (p.forward(y, x), p.inverse(z, y)), iters=200, warm=20)
+        out["C1_1d_c2c_f32_n1024_fwd_inv"] = {"us_per_pair": ms * 1e3, "gflops": 2 * 5 * 1024 * 10 / (ms * 1e-3) / 1e9}
+        # C3: N=2^24 fp64
+        n = 1 << 24
+        p = g.FFT(n, np.float64)
+        x = torch.randn(n, dtype=torch.complex128, device="cuda")
+        y = torch.empty_like(x)
+        ms = timed(lambda: p.forward(y, x))
+        out["C3_1d_c2c_f64_n2^24"] = {"ms": ms, "gflops": 5 * n * 24 / (ms * 1e-3) / 1e9,
+                                      "algorithmic_gbs": 2 * n * 16 / (ms * 1e-3) / 1e9,
+                                      "frac_of_measured_hbm": 2 * n * 16 / (ms * 1e-3) / 1e9 / peak, "plan": p.describe()}
+        del x, y
+        # C4: R2C fp32 N=2^22 x 256 (half spectrum)
+        n, b = 1 << 22, 256
+        p = g.RealFFT(n, np.float32, half=True, batch=b)
+        x = torch.randn(b, n, device="cuda")
+        y = torch.empty((b, n // 2 + 1), dtype=torch.complex64, device="cuda")
+        ms = timed(lambda: p.forward(y, x), iters=5, warm=2)
+        by = (n * 4 + (n // 2 + 1) * 8) * b
+        out["C4_1d_r2c_f32_n2^22_x256"] = {"ms": ms, "gflops_2.5NlogN": 2.5 * n * 22 * b / (ms * 1e-3) / 1e9,
+                                           "gflops_5NlogN": 5 * n * 22 * b / (ms * 1e-3) / 1e9,
+                                           "algorithmic_gbs": by / (ms * 1e-3) / 1e9,
+                                           "frac_of_measured_hbm": by / (ms * 1e-3) / 1e9 / peak, "plan": p.describe()}
+        del x, y
+        # C5 on ONE GPU (the multi-GPU slab version is bench_dist.py): 2D fp32 32768^2
+        w = h = 32768
+        p = g.FFT2D(w, h, np.float32)
+        x = torch.randn(h, w, dtype=torch.complex64, device="cuda")
+        y = torch.empty_like(x)
+        ms = timed(lambda: p.transform(y, x), iters=3, warm=1)
+        out["C5_2d_c2c_f32_32768^2_1gpu"] = {"ms": ms, "gflops": 5 * w * h * 30 / (ms * 1e-3) / 1e9,
+                                             "algorithmic_gbs": 2 * w * h * 8 / (ms * 1e-3) / 1e9,
+                                             "frac_of_measured_hbm": 2 * w * h * 8 / (ms * 1e-3) / 1e9 / peak,
+                                             "plan": p.describe()}
+    except Exception as e:
+        out["error"] = repr(e)
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

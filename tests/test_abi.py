@@ -1,0 +1,102 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads and exports every symbol include/genfft_cuda.h declares;
+host-side argument checking works without a GPU; no compute is attempted."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import genfft_b200 as g
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "genfft_cuda.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(g.LIB_PATH):
+        g.build()
+    return g.lib()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(genfft_cuda_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for must in ("genfft_cuda_plan_c2c_1d", "genfft_cuda_plan_r2c_1d", "genfft_cuda_plan_c2c_2d", "genfft_cuda_plan_vert",
+                 "genfft_cuda_plan_dit", "genfft_cuda_exec_c2c", "genfft_cuda_exec_c2c_dev", "genfft_cuda_exec_r2c",
+                 "genfft_cuda_exec_c2c_2d", "genfft_cuda_exec_vert", "genfft_cuda_exec_dit", "genfft_cuda_plan_destroy"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", g.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (genfft_cuda_[a-z0-9_]+)", out))
+    declared = set(declared_symbols())
+    assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
+    # the python binding covers the same surface, with no torch types in any signature
+    assert set(g.exported_symbols()) == declared
+    for name in declared:
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
+
+
+def test_extern_c_linkage_only_plain_types():
+    text = open(HEADER).read()
+    assert 'extern "C"' in text
+    for banned in ("torch", "at::", "std::", "cudaStream_t"):
+        body = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        assert banned not in body, f"{banned} leaked into the C ABI"
+
+
+def test_sm100a_only_binary():
+    """The product is sm_100a code: the fat binary holds sm_100a SASS and nothing for other architectures."""
+    out = subprocess.run(["cuobjdump", "-lelf", g.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_gpu_fails_loudly_or_runs(lib):
+    """Without a usable sm_100 device plan creation must fail with a CUDA error -- there is no CPU fallback."""
+    if g.device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(g.GenfftCudaError, match="error 3"):
+        g.FFT(1024)
+    with pytest.raises(g.GenfftCudaError):
+        g.RealFFT(1024)
+    with pytest.raises(g.GenfftCudaError):
+        g.FFT2D(64, 64)
+
+
+def test_argument_errors_before_any_cuda_call(lib):
+    h = ctypes.c_void_p()
+    assert lib.genfft_cuda_plan_c2c_1d(ctypes.byref(h), 0, 3, 1, 0, 0) == 1      # not a power of two -> ERR_SIZE
+    assert b"unsupported size" in lib.genfft_cuda_last_error_string()
+    assert lib.genfft_cuda_plan_c2c_1d(ctypes.byref(h), 0, 1 << 30, 1, 0, 0) == 1  # above the size cap
+    assert lib.genfft_cuda_plan_c2c_1d(ctypes.byref(h), 0, 8, 0, 0, 0) == 2      # batch < 1 -> ERR_ARG
+    assert lib.genfft_cuda_plan_c2c_1d(None, 0, 8, 1, 0, 0) == 2
+    assert lib.genfft_cuda_plan_c2c_2d(ctypes.byref(h), 0, 12, 8) == 1
+    assert lib.genfft_cuda_exec_c2c(None, None, None, 0) == 2
+    assert lib.genfft_cuda_plan_destroy(None) == 0
+
+
+def test_host_mirror_semantics_without_gpu():
+    empty = g.FFT()
+    assert not empty and empty.size() == 0           # default-constructed plan (fft.h:59,107-108)
+    assert not g.FFT2D() and g.FFT2D().cols() == 0 and g.FFT2D().rows() == 0
+    with pytest.raises(g.GenfftCudaError):
+        empty.transform(np.zeros(4, np.complex64), np.zeros(4, np.complex64))
+
+
+def test_product_never_imports_the_oracle():
+    """genfft_b200/ must not reference oracle/ in any way (the oracle is the checker, never the product)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "genfft_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "genfft_ref" not in text and "oracle/" not in text, f

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Multi-GPU benchmark of BASELINE config C5 (2D complex fp32 FFT 32768 x 32768, slab-decomposed) -- run under
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench_dist.py
+Not the driver's contract bench (that is bench.py, workload C2); prints one JSON line per transport / mode with
+the effective GFLOP/s (5*W*H*log2(W*H)/t), and the time against the NVLink all-to-all roofline of SURVEY.md 8(d):
+bytes sent per GPU per transpose = (8 GiB / P) * (P-1)/P at the measured 770 GB/s per direction (900 nominal).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from genfft_b200.dist import DistFFT2D  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=32768)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    w = h = args.size
+    hl = h // world
+    gen = torch.Generator(device="cuda").manual_seed(rank)
+    slab = torch.view_as_complex(torch.rand((hl, w, 2), generator=gen, device="cuda") * 2 - 1)
+    flop = 5.0 * w * h * math.log2(w * h)
+    sent = (w * h * 8 / world) * (world - 1) / world
+    for transport in ("nccl", "p2p"):
+        for transposed in (True, False):
+            plan = DistFFT2D(w, h, np.float32, transport=transport, transposed_out=transposed)
+            for _ in range(args.warmup):
+                plan.transform(slab)
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                plan.transform(slab)
+            b.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / args.steps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            ntr = 1 if transposed else 2
+            if rank == 0:
+                print(json.dumps({
+                    "workload": f"C5: 2D C2C fp32 {w}x{h}, slab-decomposed over {world} GPUs", "transport": transport,
+                    "output": "transposed (1 global transpose)" if transposed else "natural order (2 global transposes)",
+                    "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
+                    "alltoall_bytes_sent_per_gpu_per_transpose": sent,
+                    "nvlink_floor_ms_at_770GBs": ntr * sent / 770e9 * 1e3,
+                    "nvlink_floor_ms_at_900GBs": ntr * sent / 900e9 * 1e3,
+                    "frac_of_nvlink_roofline_770": (ntr * sent / 770e9 * 1e3) / ms,
+                }), flush=True)
+            plan.close()
+            del plan
+            torch.cuda.empty_cache()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Worker for tests/test_gpu_dist.py (launched with torch.distributed.run, one rank per GPU):
+slab-decomposed 2D FFT on small arrays, both transports, against numpy's fft2 of the full array."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from genfft_b200.dist import DistFFT2D  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    fails = 0
+    cases = [(64, 64, np.float32), (256, 128, np.float32), (2048, 512, np.float32), (512, 8192, np.float32),
+             (32768, 64, np.float32), (64, 32768, np.float32), (1024, 1024, np.float64)]
+    for w, h, dt in cases:
+        if w % world or h % world:
+            continue
+        cd = np.complex64 if dt == np.float32 else np.complex128
+        rng = np.random.default_rng(w + h)
+        full = (rng.uniform(-1, 1, (h, w)) + 1j * rng.uniform(-1, 1, (h, w))).astype(cd)
+        hl, wp = h // world, w // world
+        want_f = np.fft.fft2(full.astype(np.complex128))
+        want_i = np.fft.ifft2(full.astype(np.complex128)) * (w * h)
+        tol = (1e-6 if dt == np.float32 else 1e-14) * np.log2(w * h)
+        slab = torch.from_numpy(full[rank * hl:(rank + 1) * hl].copy()).cuda()
+        for transport in ("nccl", "p2p"):
+            for transposed in (False, True):
+                plan = DistFFT2D(w, h, dt, transport=transport, transposed_out=transposed)
+                for inv, want in ((False, want_f), (True, want_i)):
+                    for rep in range(2):  # twice: buffers are reused between calls
+                        got = plan.transform(slab, inv)
+                        torch.cuda.synchronize()
+                    got = got.cpu().numpy()
+                    ref = want[:, rank * wp:(rank + 1) * wp] if transposed else want[rank * hl:(rank + 1) * hl]
+                    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+                    ok = err <= tol
+                    fails += not ok
+                    if rank == 0 or not ok:
+                        print(f"[rank {rank}] {w}x{h} {dt.__name__} {transport} transposed={transposed} inv={inv}: "
+                              f"rel-L2 {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+                dist.barrier()
+                plan.close()
+    t = torch.tensor([fails], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("DIST PASSED" if t.item() == 0 else f"DIST FAILED ({t.item()})", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -237,6 +237,45 @@ static int stage_twiddle_table(int device, int precision, const KernelEntry* k, 
   return GENFFT_CUDA_OK;
 }
 
+// inter-pass factor W_{P*Ns}^(p*i) laid out [i][p] (see PassParams::tw_b)
+static std::map<std::tuple<int, int, int, long long>, void*> g_pass_tables;
+
+static int pass_stage_table(int device, int precision, int P, long long Ns, const void** out) {
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_tuple(device, precision, P, Ns);
+  auto it = g_pass_tables.find(key);
+  if (it != g_pass_tables.end()) {
+    *out = it->second;
+    return GENFFT_CUDA_OK;
+  }
+  const size_t es = elem_size(precision);
+  const size_t count = (size_t)P * (size_t)Ns;
+  std::vector<unsigned char> host(es * count);
+  // row i is W_{P*Ns}^(p*i): fill row 1 exactly, the others by exact index arithmetic (p*i mod P*Ns)
+  const unsigned long long M = (unsigned long long)P * (unsigned long long)Ns;
+  for (int i = 0; i < P; i++)
+    for (long long q = 0; q < Ns; q++) {
+      long double c, sn;
+      unit_root(((unsigned long long)q * (unsigned long long)i) % M, M, &c, &sn);
+      const size_t e = (size_t)i * (size_t)Ns + (size_t)q;
+      if (precision == GENFFT_CUDA_F32) {
+        float* t = reinterpret_cast<float*>(host.data()) + 2 * e;
+        t[0] = (float)c;
+        t[1] = (float)-sn;
+      } else {
+        double* t = reinterpret_cast<double*>(host.data()) + 2 * e;
+        t[0] = (double)c;
+        t[1] = (double)-sn;
+      }
+    }
+  void* d = nullptr;
+  CU_TRY(cudaMalloc(&d, host.size()));
+  CU_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+  g_pass_tables[key] = d;
+  *out = d;
+  return GENFFT_CUDA_OK;
+}
+
 // two-level table for W_M^e, e < M: W = hi[e >> shift] * lo[e & (2^shift - 1)]
 static int two_level_table(int device, int precision, long long M, const void** hi, const void** lo, int* shift) {
   const int lg = ilog2(M);
@@ -293,6 +332,9 @@ static int build_seq(Seq* seq, int device, int precision, long long N, bool wide
     if (Ns > 1) {
       rc = two_level_table(device, precision, Ns * ps.R, &ps.tw_hi, &ps.tw_lo, &ps.tw_shift);
       if (rc) return rc;
+      // W_{P*Ns}^(p*i), i < P, p < Ns, laid out [i][p]
+      rc = pass_stage_table(device, precision, ps.k->P, Ns, &ps.tw_b);
+      if (rc) return rc;
     }
     seq->passes.push_back(ps);
     Ns *= ps.R;
@@ -317,6 +359,8 @@ static PassParams base_params(const PassSpec& ps, const void* in, void* out, int
   p.tw_hi = ps.tw_hi;
   p.tw_lo = ps.tw_lo;
   p.tw_shift = ps.tw_shift;
+  p.tw_b = ps.tw_b;
+  p.tw_b_stride = ps.Ns;
   return p;
 }
 

@@ -19,6 +19,7 @@ struct PassSpec {
   const void* tw_hi = nullptr;  // inter-pass twiddle W_{Ns*R} (null for the first pass)
   const void* tw_lo = nullptr;
   int tw_shift = 0;
+  const void* tw_b = nullptr;   // W_{P*Ns}^(p*i) laid out [i][p]
 };
 
 // decomposition of one length-N transform

@@ -47,10 +47,14 @@ struct PassParams {
   //   offset = brev(t1*g_t1 + col*g_c + idx*g_i, brev_bits) * brev_stride + t0*in_t0 + col*in_stride_c
   int brev_bits;
   long long g_t1, g_c, g_i, brev_stride;
-  // inter-pass Stockham twiddle W_M^(p*idx), p = t1*p_t1 + col*p_c, two-level table
+  // inter-pass Stockham twiddle W_M^(p*idx), M = Ns*L, p = t1*p_t1 + col*p_c, idx = u + i*TN, factored as
+  //   W_M^(p*u)            one per thread, two-level table:  tw_hi[e >> tw_shift] * tw_lo[e & mask], e = p*u
+  //   W_M^(p*i*TN)         = W_{P*Ns}^(p*i), table tw_b[i*tw_b_stride + p] (lanes read consecutive p: coalesced)
   const void* tw_hi;
   const void* tw_lo;
-  int tw_shift;     // e = p*idx ; W = tw_hi[e >> tw_shift] * tw_lo[e & ((1<<tw_shift)-1)]
+  int tw_shift;
+  const void* tw_b;
+  long long tw_b_stride;  // = Ns
   int p_t1, p_c;
   uint32_t p_mask;  // p &= p_mask
   // on-chip stage twiddles, one block per radix stage s >= 1 laid out [q][p]:
@@ -146,15 +150,20 @@ struct TileKernel {
     const uint32_t p = (t.p_base + col * (uint32_t)prm.p_c) & prm.p_mask;
     const V* hi = reinterpret_cast<const V*>(prm.tw_hi);
     const V* lo = reinterpret_cast<const V*>(prm.tw_lo);
-    const uint32_t lomask = (1u << prm.tw_shift) - 1u;
+    const uint32_t e = p * (uint32_t)u;
+    V ah = __ldg(hi + (e >> prm.tw_shift));
+    V al = __ldg(lo + (e & ((1u << prm.tw_shift) - 1u)));
+    const cpx<T> a = cmul(cpx<T>(ah.x, ah.y), cpx<T>(al.x, al.y));  // W_M^(p*u)
+    const V* tb = reinterpret_cast<const V*>(prm.tw_b) + p;
+    V b[P];
 #pragma unroll
-    for (int i = 0; i < P; i++) {
-      const uint32_t e = p * (uint32_t)(u + i * TN);
-      V a = __ldg(hi + (e >> prm.tw_shift));
-      V b = __ldg(lo + (e & lomask));
-      cpx<T> w = cmul(cpx<T>(a.x, a.y), cpx<T>(b.x, b.y));
-      x[i] = cmul(x[i], w);
+    for (int i = 1; i < P; i++) {
+      tb += prm.tw_b_stride;
+      b[i] = __ldg(tb);
     }
+    x[0] = cmul(x[0], a);
+#pragma unroll
+    for (int i = 1; i < P; i++) x[i] = cmul(x[i], cmul(a, cpx<T>(b[i].x, b[i].y)));
   }
 
   static __device__ __forceinline__ void load(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {

@@ -22,15 +22,19 @@ void register_kernels_f32_small(std::vector<KernelEntry>& v) {
   ADD_B(float, 32, 16, 64);
   ADD_B(float, 64, 16, 32);
   ADD_B(float, 128, 16, 16);
+  ADD_W(float, 128, 16, 32);
   ADD_B(float, 256, 16, 16);
+  ADD_W(float, 256, 16, 32);
 }
 #elif GENFFT_KSET == 1
 void register_kernels_f32_mid(std::vector<KernelEntry>& v) {
   ADD_N(float, 512, 16, 8);
   ADD_W(float, 512, 16, 16);
   ADD_N(float, 1024, 16, 4);
+  ADD_W(float, 1024, 16, 8);
   ADD_W(float, 1024, 16, 16);
   ADD_N(float, 2048, 16, 2);
+  ADD_W(float, 2048, 16, 4);
   ADD_W(float, 2048, 16, 8);
 }
 #elif GENFFT_KSET == 2
@@ -50,12 +54,15 @@ void register_kernels_f64_small(std::vector<KernelEntry>& v) {
   ADD_B(double, 32, 16, 64);
   ADD_B(double, 64, 16, 32);
   ADD_B(double, 128, 16, 16);
-  ADD_N(double, 256, 16, 8);
+  ADD_B(double, 256, 16, 8);
   ADD_W(double, 256, 16, 16);
+  ADD_W(double, 256, 8, 16);
+  ADD_W(double, 128, 8, 16);
 }
 #elif GENFFT_KSET == 4
 void register_kernels_f64_mid(std::vector<KernelEntry>& v) {
   ADD_B(double, 512, 16, 8);
+  ADD_W(double, 512, 8, 8);
   ADD_N(double, 1024, 16, 4);
   ADD_W(double, 1024, 16, 8);
   ADD_N(double, 2048, 16, 2);

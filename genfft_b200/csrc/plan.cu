@@ -98,12 +98,23 @@ static std::vector<KernelEntry>& registry(int precision) {
   return precision == GENFFT_CUDA_F32 ? f32 : f64;
 }
 
-// wide = prefer the largest C (column passes), else the smallest (contiguous batched)
+// wide = prefer the largest C (column passes), else the smallest (contiguous batched).
+// Tuning knobs: GENFFT_CUDA_WIDE_C_{F32,F64} caps C of wide kernels, GENFFT_CUDA_P_{F32,F64} picks the
+// points-per-thread variant where several are compiled (default 16).
 static const KernelEntry* find_kernel(int precision, long long L, bool wide) {
+  const bool f32 = precision == GENFFT_CUDA_F32;
+  const int cap = wide ? env_int(f32 ? "GENFFT_CUDA_WIDE_C_F32" : "GENFFT_CUDA_WIDE_C_F64", 1 << 30) : 1 << 30;
+  const int want_p = wide ? env_int(f32 ? "GENFFT_CUDA_P_F32" : "GENFFT_CUDA_P_F64", 16) : 16;
   const KernelEntry* best = nullptr;
-  for (auto& e : registry(precision)) {
-    if (e.L != L) continue;
-    if (!best || (wide ? e.C > best->C : e.C < best->C)) best = &e;
+  for (int pass = 0; pass < 2 && !best; pass++) {
+    for (auto& e : registry(precision)) {
+      if (e.L != L) continue;
+      if (wide && !e.launch[M_COL][0]) continue;
+      if (!wide && !e.launch[M_ROW][0]) continue;
+      if (pass == 0 && (e.P != want_p && L >= 16)) continue;   // preferred P first
+      if (pass == 0 && wide && e.C > cap) continue;
+      if (!best || (wide ? e.C > best->C : e.C < best->C)) best = &e;
+    }
   }
   return best;
 }
@@ -292,7 +303,7 @@ static int two_level_table(int device, int precision, long long M, const void** 
 // sequence decomposition
 // ------------------------------------------------------------------------------------------------
 static long long max_single_len(int precision, bool wide) {
-  if (wide) return env_int(precision == GENFFT_CUDA_F32 ? "GENFFT_CUDA_WIDE_SINGLE_F32" : "GENFFT_CUDA_WIDE_SINGLE_F64", 4096);
+  if (wide) return env_int(precision == GENFFT_CUDA_F32 ? "GENFFT_CUDA_WIDE_SINGLE_F32" : "GENFFT_CUDA_WIDE_SINGLE_F64", 2048);
   return precision == GENFFT_CUDA_F32 ? 16384 : 8192;
 }
 static long long max_pass_len(int precision) {
@@ -582,6 +593,7 @@ static void seq_steps(const Seq& seq, bool col, std::vector<Step>& steps, bool b
     st.N = seq.N;
     st.col = col;
     st.safe = (m == 1) || (s == m - 1);
+    if (m > 1 && env_int("GENFFT_CUDA_NO_INPLACE", 0)) st.safe = false;
     st.brev = brev_first && s == 0;
     st.real_in = real_first && s == 0;
     if (st.brev || st.real_in) st.safe = st.safe && m == 1;

@@ -28,10 +28,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) dit_kernel(const __grid_constant__ DitParams p) {
   using V = typename vec2<T>::type;
   const int N = p.n;
-  const long long b = blockIdx.y;
+  const int quarter = N >> 2;
+  for (long long b = blockIdx.y; b < p.batch; b += gridDim.y) {
   const V* Z = reinterpret_cast<const V*>(p.in) + b * p.in_dist;
   V* F = reinterpret_cast<V*>(p.out) + b * p.out_dist;
-  const int quarter = N >> 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= quarter; i += gridDim.x * blockDim.x) {
     if (i == 0) {
       if (p.in_is_real_scalar) {  // RealFFT n == 1 (FFTReal.h:206-207)
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256) dit_kernel(const __grid_constant__ DitPar
         F[N - j] = cj;
       }
     }
+  }
   }
 }
 

@@ -122,7 +122,7 @@ static const KernelEntry* find_kernel(int precision, long long L, bool wide) {
 static std::mutex g_cfg_mu;
 static std::map<std::pair<int, const void*>, int> g_occupancy;  // (device, func) -> CTAs per SM
 
-static int kernel_occupancy(const KernelEntry* k, const void* func, int device, int* out) {
+static int kernel_occupancy(const KernelEntry* k, const void* func, size_t smem, int device, int* out) {
   std::lock_guard<std::mutex> lk(g_cfg_mu);
   auto key = std::make_pair(device, func);
   auto it = g_occupancy.find(key);
@@ -130,11 +130,11 @@ static int kernel_occupancy(const KernelEntry* k, const void* func, int device, 
     *out = it->second;
     return GENFFT_CUDA_OK;
   }
-  if (k->smem > 48 * 1024)
-    CU_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+  if (smem > 48 * 1024)
+    CU_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int n = 0;
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, func, k->threads, k->smem));
-  if (n < 1) return fail(GENFFT_CUDA_ERR_CUDA, "kernel L=%d C=%d cannot be resident (smem %zu)", k->L, k->C, k->smem);
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, func, k->threads, smem));
+  if (n < 1) return fail(GENFFT_CUDA_ERR_CUDA, "kernel L=%d C=%d cannot be resident (smem %zu)", k->L, k->C, smem);
   g_occupancy[key] = n;
   *out = n;
   return GENFFT_CUDA_OK;
@@ -500,7 +500,12 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
   const int inv = p.inverse ? 1 : 0;
   if (mode < 0 || mode >= kNumModes || !ps.k->launch[mode][inv]) mode = M_GEN;
   int occ = 1;
-  int rc = kernel_occupancy(ps.k, ps.k->func[mode][inv], plan->device, &occ);
+  // TMA prefetch (cp.async.bulk) needs 16-byte aligned rows and pays off with several tiles per CTA
+  if (mode == M_ROW && ps.k->launch[M_ROWTMA][inv] && env_int("GENFFT_CUDA_TMA", 1) &&
+      ((uintptr_t)p.in % 16 == 0) && ((p.in_stride_c * (long long)elem_size(plan->precision)) % 16 == 0) &&
+      p.ntiles >= 4u * (uint32_t)plan->num_sms)
+    mode = M_ROWTMA;
+  int rc = kernel_occupancy(ps.k, ps.k->func[mode][inv], ps.k->smem_mode[mode], plan->device, &occ);
   if (rc) return rc;
   long long cap = (long long)plan->num_sms * occ;
   int grid = (int)std::min<long long>(p.ntiles, cap);
@@ -540,7 +545,7 @@ static int launch_dit(const Plan* plan, void* out, long long out_dist, const voi
   d.tw_lo = plan->dit_lo;
   d.tw_shift = plan->dit_shift;
   const int work = n / 4 + 1;
-  dim3 grid((unsigned)std::min((work + 255) / 256, 4096), (unsigned)batch);
+  dim3 grid((unsigned)std::min((work + 255) / 256, 4096), (unsigned)std::min<long long>(batch, 65535));
   if (plan->precision == GENFFT_CUDA_F32)
     dit_kernel<float><<<grid, 256, 0, stream>>>(d);
   else
@@ -611,10 +616,17 @@ struct FinalStore {
   long long peer_offset = 0;  // elements added to every peer pointer
 };
 
+// Optional fusion of the real-FFT split into the last pass of a multi-pass chain (M_COLTWDIT).
+struct DitFuse {
+  int half = 0;
+  const void* dit_a = nullptr;   // W_n^p, p < Ns of the last pass
+  const void* dit_tw = nullptr;  // W_{2L}^k, k < L of the last pass
+};
+
 // runs `steps`; count = batch (1D) or rows (row passes of 2D); cols = columns for column passes
 static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, long long scratch_pitch,
                      size_t scratch_elems, long long count, long long cols, int inverse, cudaStream_t stream,
-                     const FinalStore* fs = nullptr) {
+                     const FinalStore* fs = nullptr, const DitFuse* df = nullptr) {
   std::vector<Step> steps(steps_in);
   if (fs && steps.size() > 1) steps.back().safe = false;  // the last pass writes elsewhere than it reads
   const size_t es = elem_size(plan->precision);
@@ -673,6 +685,15 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     if (st.real_in) {
       p.in_real = 1;
       p.mode = M_GEN;
+    }
+    if (df && s == n - 1) {
+      // pair tiles: Ns/C tiles of {p} U {Ns-p} plus one tile for column 0
+      p.mode = M_COLTWDIT;
+      p.n2 = (uint32_t)(st.ps->Ns / st.ps->k->C) + 1u;
+      p.ntiles = (uint32_t)(count * p.n2);
+      p.dit_half = df->half;
+      p.dit_a = df->dit_a;
+      p.dit_tw = df->dit_tw;
     }
     if (fs && s == n - 1) {
       p.mode = M_GEN;
@@ -778,6 +799,15 @@ int genfft_cuda_plan_r2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
   }
   rc = build_seq(&p->seq, p->device, precision, n >= 2 ? n / 2 : 1, false);
   if (!rc && n >= 8) rc = two_level_table(p->device, precision, n, &p->dit_hi, &p->dit_lo, &p->dit_shift);
+  if (!rc && n >= 4 && p->seq.passes.size() == 1)  // W_n^k, k < n/2, for the fused split
+    rc = twiddle_table(p->device, precision, n, 1, n / 2, &p->dit_full);
+  if (!rc && p->seq.passes.size() > 1) {
+    const PassSpec& last = p->seq.passes.back();
+    if (last.k->launch[M_COLTWDIT][0] && last.Ns % last.k->C == 0 && last.Ns * last.R == n / 2) {
+      rc = twiddle_table(p->device, precision, n, 1, last.Ns, &p->dit_a);
+      if (!rc) rc = twiddle_table(p->device, precision, 2 * last.R, 1, last.R, &p->dit_b);
+    }
+  }
   if (!rc && n < 8) rc = two_level_table(p->device, precision, 8, &p->dit_hi, &p->dit_lo, &p->dit_shift);
   if (rc) {
     delete p;
@@ -882,7 +912,8 @@ int genfft_cuda_plan_describe(genfft_cuda_plan_t plan, char* buf, size_t buflen)
   };
   add_seq(plan->kind == PLAN_C2C_2D ? "rows" : "seq", plan->seq);
   if (plan->kind == PLAN_C2C_2D) add_seq(" cols", plan->seq_v);
-  if (plan->kind == PLAN_R2C_1D) s += " +dit";
+  if (plan->kind == PLAN_R2C_1D)
+    s += (plan->dit_full || plan->dit_a) ? " +split fused into the last pass" : " +split kernel";
   snprintf(buf, buflen, "%s", s.c_str());
   return GENFFT_CUDA_OK;
 }
@@ -927,9 +958,27 @@ int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t st, long 
   if (n <= 2) {  // no complex sub-transform: the split reads the input directly (FFTReal.h:206-207)
     return launch_dit(p, out, p->out_dist, in, n == 1 ? p->in_dist : p->in_dist / 2, (int)n, p->half, batch, n == 1, st);
   }
+  // n/2 fits on chip: one kernel does the packed complex transform and the split (fused real-FFT post-process)
+  if (p->seq.passes.size() == 1 && p->dit_full && p->seq.passes[0].k->launch[M_ROWDIT][0] &&
+      env_int("GENFFT_CUDA_FUSED_DIT", 1) && out != in) {
+    const PassSpec& ps = p->seq.passes[0];
+    PassParams pp = emit_1d(ps, n / 2, in, p->in_dist / 2, out, p->out_dist, batch, 0, false);
+    pp.mode = M_ROWDIT;
+    pp.dit_tw = p->dit_full;
+    pp.dit_half = p->half;
+    return launch_pass(p, ps, pp, st);
+  }
   std::vector<Step> steps;
   seq_steps(p->seq, false, steps, false, false);
   View vin{const_cast<void*>(in), p->in_dist / 2}, vout{out, p->out_dist};
+  // multi-pass: the split is fused into the last pass, which then works on pairs of column groups
+  if (p->seq.passes.size() > 1 && p->dit_a && env_int("GENFFT_CUDA_FUSED_DIT", 1)) {
+    DitFuse df;
+    df.half = p->half;
+    df.dit_a = p->dit_a;
+    df.dit_tw = p->dit_b;
+    return run_chain(p, steps, vin, vout, n / 2, (size_t)(n / 2) * batch, batch, 0, 0, st, nullptr, &df);
+  }
   int rc = run_chain(p, steps, vin, vout, n / 2, (size_t)(n / 2) * batch, batch, 0, 0, st);
   if (rc) return rc;
   return launch_dit(p, out, p->out_dist, out, p->out_dist, (int)n, p->half, batch, false, st);

@@ -44,6 +44,9 @@ struct Plan {
   const void* dit_hi = nullptr;
   const void* dit_lo = nullptr;
   int dit_shift = 0;
+  const void* dit_a = nullptr;     // W_n^p, p < Ns(last pass)      (fused split, multi-pass plans)
+  const void* dit_b = nullptr;     // W_{2L}^k, k < L(last pass)
+  const void* dit_full = nullptr;  // W_n^k, k < n/2 (fused split, single-pass plans)
   // scratch (device), lazily grown
   std::mutex mu;
   void* scratch = nullptr;

@@ -6,12 +6,13 @@
 
 namespace genfft_cuda {
 
-constexpr int kNumModes = 5;
+constexpr int kNumModes = 8;
 
 struct KernelEntry {
   int L, P, C;
   int threads;
   size_t smem;
+  size_t smem_mode[kNumModes];  // dynamic shared memory of each compiled mode (TMA mode adds an input buffer)
   // [mode][inverse]; null when that variant is not compiled for this shape (M_GEN always is, with
   // the direction taken at run time, stored in both slots)
   const void* func[kNumModes][2];
@@ -26,6 +27,12 @@ void launch_tile(const PassParams& prm, int grid, cudaStream_t stream) {
 
 template <typename T, int L, int P, int C, int MODE>
 void add_mode(KernelEntry& e) {
+  e.smem_mode[MODE] = TileKernel<T, L, P, C, MODE, false>::SMEM_BYTES;
+  if (MODE == M_ROWDIT || MODE == M_COLTWDIT) {  // forward only
+    e.func[MODE][0] = reinterpret_cast<const void*>(&fft_tile_kernel<T, L, P, C, MODE, false>);
+    e.launch[MODE][0] = &launch_tile<T, L, P, C, MODE, false>;
+    return;
+  }
   e.func[MODE][0] = reinterpret_cast<const void*>(&fft_tile_kernel<T, L, P, C, MODE, false>);
   e.launch[MODE][0] = &launch_tile<T, L, P, C, MODE, false>;
   if (MODE == M_GEN) {
@@ -48,11 +55,17 @@ KernelEntry make_entry() {
   e.threads = K::THREADS;
   e.smem = K::SMEM_BYTES;
   add_mode<T, L, P, C, M_GEN>(e);
-  if constexpr (NARROW) add_mode<T, L, P, C, M_ROW>(e);
+  if constexpr (NARROW) {
+    add_mode<T, L, P, C, M_ROW>(e);
+    add_mode<T, L, P, C, M_ROWDIT>(e);
+    if constexpr (L >= 256 && TileKernel<T, L, P, C, M_ROWTMA, false>::SMEM_BYTES <= 200 * 1024)
+      add_mode<T, L, P, C, M_ROWTMA>(e);
+  }
   if constexpr (WIDE) {
     add_mode<T, L, P, C, M_COL>(e);
     add_mode<T, L, P, C, M_COLTW>(e);
     add_mode<T, L, P, C, M_FIRST>(e);
+    if constexpr (C >= 2 && L >= 16) add_mode<T, L, P, C, M_COLTWDIT>(e);
   }
   return e;
 }

@@ -55,6 +55,13 @@ struct PassParams {
   int tw_shift;
   const void* tw_b;
   long long tw_b_stride;  // = Ns
+  // fused real-FFT split (M_ROWDIT): the tile's L-point complex transforms are the packed halves of 2L-point
+  // real signals; dit_tw[k] = W_{2L}^k, k < L; dit_half: write L+1 bins only, else all 2L
+  const void* dit_tw;
+  int dit_half;
+  // M_COLTWDIT: the L-point pass is the last of an M = Ns*L point packed transform (n = 2M real points):
+  //   W_n^(p + k*Ns) = dit_a[p] * dit_tw[k],  dit_a[p] = W_n^p (p < Ns),  dit_tw[k] = W_{2L}^k (k < L)
+  const void* dit_a;
   int p_t1, p_c;
   uint32_t p_mask;  // p &= p_mask
   // on-chip stage twiddles, one block per radix stage s >= 1 laid out [q][p]:
@@ -98,7 +105,42 @@ __host__ __device__ constexpr int tile_pitch(int L) { return pad_idx(L) | 1; }
 //   M_COL   : strided in and out, lanes across columns                (FFTVert, 2D columns, last pass)
 //   M_COLTW : M_COL + inter-pass Stockham twiddle fused into the load (later passes of a large N)
 //   M_FIRST : strided in (lanes across columns), unit-stride out      (first pass of a large N)
-enum Mode { M_GEN = 0, M_ROW = 1, M_COL = 2, M_COLTW = 3, M_FIRST = 4 };
+//   M_ROWTMA: M_ROW with the next tile prefetched by cp.async.bulk (TMA) into a second shared buffer while
+//             the current one is transformed; an mbarrier signals arrival        (batched contiguous 1D)
+//   M_ROWDIT: M_ROW + the real-FFT split fused after the last butterfly stage    (RealFFT<T>, n <= 2*Lmax)
+//   M_COLTWDIT: last pass of a large real transform: M_COLTW on a PAIR of column groups {p} and {Ns-p} so that the
+//             real-FFT split, which couples bins q and M-q, is fused after the last butterfly stage
+enum Mode { M_GEN = 0, M_ROW = 1, M_COL = 2, M_COLTW = 3, M_FIRST = 4, M_ROWTMA = 5, M_ROWDIT = 6, M_COLTWDIT = 7 };
+
+// ---- mbarrier / bulk-copy PTX (sm_90+; SASS: SYNCS / UBLKCP) ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 template <typename T, int L, int P, int C, int MODE, bool INV>
 struct TileKernel {
@@ -106,10 +148,18 @@ struct TileKernel {
   static constexpr int THREADS = TN * C;
   static constexpr int NST = num_stages(L, P);
   static constexpr int PITCH = tile_pitch(L);
-  static constexpr size_t SMEM_BYTES = NST > 1 ? sizeof(cpx<T>) * (size_t)PITCH * C : 0;
+  static constexpr bool TMA = MODE == M_ROWTMA;
+  static constexpr bool DIT = MODE == M_ROWDIT;
+  static constexpr bool PAIR = MODE == M_COLTWDIT;
+  static constexpr int HALF_C = C / 2;
+  static constexpr bool ROWLIKE = MODE == M_ROW || TMA || DIT;
+  static constexpr size_t XBUF_BYTES = (NST > 1 || DIT || PAIR) ? sizeof(cpx<T>) * (size_t)PITCH * C : 0;
+  // TMA mode: [exchange buffer][input buffer C*L][mbarrier]
+  static constexpr size_t INBUF_OFFSET = (XBUF_BYTES + 127) & ~(size_t)127;
+  static constexpr size_t SMEM_BYTES = TMA ? INBUF_OFFSET + sizeof(cpx<T>) * (size_t)L * C + 16 : XBUF_BYTES;
   static constexpr bool GEN = MODE == M_GEN;
-  static constexpr bool UNIT_IN = MODE == M_ROW;
-  static constexpr bool UNIT_OUT = MODE == M_ROW || MODE == M_FIRST;
+  static constexpr bool UNIT_IN = ROWLIKE;
+  static constexpr bool UNIT_OUT = ROWLIKE || MODE == M_FIRST;
   using V = typename vec2<T>::type;
 
   static __device__ __forceinline__ uint32_t brev(uint32_t v, int bits) { return __brev(v) >> (32 - bits); }
@@ -123,7 +173,7 @@ struct TileKernel {
 
   static __device__ __forceinline__ Tile decode(const PassParams& prm, uint32_t tile) {
     Tile t;
-    if constexpr (MODE == M_ROW) {  // columns are whole transforms; no outer tile indices
+    if constexpr (ROWLIKE) {  // columns are whole transforms; no outer tile indices
       t.col0 = tile * C;
       t.in_off = t.out_off = 0;
       t.p_base = 0;
@@ -141,6 +191,27 @@ struct TileKernel {
     if (GEN && prm.brev_bits) t.in_off = (long long)t0 * prm.in_t0;
     }
     return t;
+  }
+
+  // column (sequence index within the tile enumeration) handled by lane-column c of this tile
+  static __device__ __forceinline__ uint32_t column_of(const PassParams& prm, const Tile& t, int c, bool& valid) {
+    if constexpr (PAIR) {
+      // pair tile j: columns {j*H+1 .. (j+1)*H} and their mirrors {Ns-(j+1)*H .. Ns-j*H-1}; the extra last tile is
+      // column 0 alone (its bins pair with themselves).  Ns/2 would appear twice: its mirror-side copy is masked.
+      const uint32_t Ns = (uint32_t)prm.ncols;
+      const uint32_t j = t.col0 / C;
+      if (j == Ns / C) {
+        valid = (c == 0);
+        return 0;
+      }
+      const uint32_t p = c < HALF_C ? j * HALF_C + 1 + c : Ns - (j + 1) * HALF_C + (c - HALF_C);
+      valid = !(c >= HALF_C && p == Ns / 2);
+      return p;
+    } else {
+      const uint32_t col = t.col0 + c;
+      valid = col < (uint32_t)prm.ncols;
+      return col;
+    }
   }
 
   static __device__ __forceinline__ bool is_inverse(const PassParams& prm) { return GEN ? prm.inverse != 0 : INV; }
@@ -167,8 +238,8 @@ struct TileKernel {
   }
 
   static __device__ __forceinline__ void load(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {
-    const uint32_t col = t.col0 + c;
-    const bool valid = col < (uint32_t)prm.ncols;
+    bool valid;
+    const uint32_t col = column_of(prm, t, c, valid);
     const long long base = t.in_off + (long long)col * prm.in_stride_c;
     if constexpr (!GEN) {
       if (valid) {
@@ -193,7 +264,7 @@ struct TileKernel {
 #pragma unroll
         for (int i = 0; i < P; i++) x[i] = cpx<T>(T(0), T(0));
       }
-      if constexpr (MODE == M_COLTW) apply_pass_twiddle(prm, t, col, u, x);
+      if constexpr (MODE == M_COLTW || PAIR) apply_pass_twiddle(prm, t, col, u, x);
     } else {
 #pragma unroll
     for (int i = 0; i < P; i++) {
@@ -362,22 +433,194 @@ struct TileKernel {
     }
   }
 
+  // ---- fused real-FFT split (adjust_DIT_impl, include/genFFT/generic/fft_dit_impl_generic.inl:27-61) ----
+  // Every thread holds bins k = u + i*TN of Z (the L-point transform of the packed real signal).  The tile is
+  // parked in shared memory so that each thread can fetch the partner bins Z[L-k]; then for all k in [0, L):
+  //   X[k] = E - t*O,  E = (Z[k] + conj Z[L-k])/2,  O = (Z[k] - conj Z[L-k])/2,  t = i*W_{2L}^k = (sin, cos)
+  // (the reference's formula for i < L/2; for the upper half it is algebraically the reference's
+  // conj(E_j + t_j O_j)), plus X[L] = Re Z0 - Im Z0, and the conjugate mirror when !half.
+  static __device__ __forceinline__ void dit_store(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P],
+                                                   cpx<T>* smem) {
+    V* sm = reinterpret_cast<V*>(smem + (size_t)c * PITCH);
+    if (NST > 1) __syncthreads();  // the last gather of the exchange buffer is complete
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      V v;
+      v.x = x[i].x;
+      v.y = x[i].y;
+      sm[pad_idx(u + i * TN)] = v;
+    }
+    __syncthreads();
+    const uint32_t col = t.col0 + c;
+    if (col >= (uint32_t)prm.ncols) return;
+    V* dst = reinterpret_cast<V*>(prm.out) + (long long)col * prm.out_stride_c;
+    const V* tw = reinterpret_cast<const V*>(prm.dit_tw);
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int k = u + i * TN;
+      const int kp = (L - k) & (L - 1);
+      const V zp = sm[pad_idx(kp)];
+      const V w = __ldg(tw + k);
+      const T er = (x[i].x + zp.x) * T(0.5), ei = (x[i].y - zp.y) * T(0.5);
+      const T orr = (x[i].x - zp.x) * T(0.5), oi = (x[i].y + zp.y) * T(0.5);
+      const T tr = -w.y, ti = w.x;
+      V f;
+      f.x = er - (tr * orr - ti * oi);
+      f.y = ei - (tr * oi + ti * orr);
+      if (k == 0) {
+        f.y = T(0);  // exactly real, as in the reference (F[0] = zeroval)
+        V nyq;
+        nyq.x = x[i].x - x[i].y;
+        nyq.y = T(0);
+        dst[L] = nyq;
+      }
+      dst[k] = f;
+      if (!prm.dit_half && k != 0) {
+        V g;
+        g.x = f.x;
+        g.y = -f.y;
+        dst[2 * L - k] = g;
+      }
+    }
+  }
+
+  // ---- fused real-FFT split for the last pass of a multi-pass transform (see M_COLTWDIT) ----
+  // Thread (c, u) holds bins q = p + k*Ns, k = u + i*TN, of column p; the partner bin M - q lives in column Ns - p
+  // (lane-column C-1-c of the same tile) at k' = L-1-k; column 0 and column Ns/2 pair with themselves.
+  static __device__ __forceinline__ void pair_dit_store(const PassParams& prm, const Tile& t, int c, int u,
+                                                        cpx<T> (&x)[P], cpx<T>* smem) {
+    if (NST > 1) __syncthreads();
+    {
+      V* sm = reinterpret_cast<V*>(smem + (size_t)c * PITCH);
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        V v;
+        v.x = x[i].x;
+        v.y = x[i].y;
+        sm[pad_idx(u + i * TN)] = v;
+      }
+    }
+    __syncthreads();
+    bool valid;
+    const uint32_t p = column_of(prm, t, c, valid);
+    if (!valid) return;
+    const uint32_t Ns = (uint32_t)prm.ncols;
+    const bool self = (p == 0) || (p == Ns / 2);
+    const int cp = self ? c : C - 1 - c;
+    const V* smp = reinterpret_cast<const V*>(smem + (size_t)cp * PITCH);
+    V* dst = reinterpret_cast<V*>(prm.out) + t.out_off;
+    const V av = __ldg(reinterpret_cast<const V*>(prm.dit_a) + p);
+    const cpx<T> a(av.x, av.y);
+    const V* tw = reinterpret_cast<const V*>(prm.dit_tw);
+    const long long M = (long long)Ns * L;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int k = u + i * TN;
+      const int kp = (p == 0) ? ((L - k) & (L - 1)) : (L - 1 - k);
+      const V zp = smp[pad_idx(kp)];
+      const V bv = __ldg(tw + k);
+      const cpx<T> w = cmul(a, cpx<T>(bv.x, bv.y));  // W_n^q
+      const T er = (x[i].x + zp.x) * T(0.5), ei = (x[i].y - zp.y) * T(0.5);
+      const T orr = (x[i].x - zp.x) * T(0.5), oi = (x[i].y + zp.y) * T(0.5);
+      const T tr = -w.y, ti = w.x;
+      V f;
+      f.x = er - (tr * orr - ti * oi);
+      f.y = ei - (tr * oi + ti * orr);
+      const long long q = (long long)p + (long long)k * Ns;
+      if (q == 0) {
+        f.y = T(0);
+        V nyq;
+        nyq.x = x[i].x - x[i].y;
+        nyq.y = T(0);
+        dst[M] = nyq;
+      }
+      dst[q] = f;
+      if (!prm.dit_half && q != 0) {
+        V g;
+        g.x = f.x;
+        g.y = -f.y;
+        dst[2 * M - q] = g;
+      }
+    }
+  }
+
   static __device__ __forceinline__ void body(const PassParams& prm, cpx<T>* smem) {
     const int tid = threadIdx.x;
-    const bool ld_b = GEN ? prm.map_load != 0 : MODE == M_ROW;
-    const bool st_b = GEN ? prm.map_store != 0 : (MODE == M_ROW || MODE == M_FIRST);
+    const bool ld_b = GEN ? prm.map_load != 0 : ROWLIKE;
+    const bool st_b = GEN ? prm.map_store != 0 : (ROWLIKE || MODE == M_FIRST);
     const int c_ld = ld_b ? tid / TN : tid % C;
     const int u_ld = ld_b ? tid % TN : tid / C;
     const int c_st = st_b ? tid / TN : tid % C;
     const int u_st = st_b ? tid % TN : tid / C;
     cpx<T> x[P];
-    for (uint32_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-      Tile t = decode(prm, tile);
-      load(prm, t, c_ld, u_ld, x);
-      int c = c_ld, u = u_ld;
-      run_stages<0>(prm, x, smem, c, u, c_st, u_st);
-      store(prm, t, c, u, x);
-      if (NST > 1) __syncthreads();  // next tile's first scatter must not overtake this tile's gathers
+    if constexpr (TMA) {
+      // Persistent CTA: tile k+1 is fetched by one cp.async.bulk per sequence into `inbuf` while tile k is being
+      // transformed.  `inbuf` is free again once every thread has copied its points to registers, which the first
+      // __syncthreads of the stage pipeline guarantees.
+      cpx<T>* inbuf = reinterpret_cast<cpx<T>*>(reinterpret_cast<unsigned char*>(smem) + INBUF_OFFSET);
+      uint64_t* bar = reinterpret_cast<uint64_t*>(inbuf + (size_t)L * C);
+      const V* gin = reinterpret_cast<const V*>(prm.in);
+      auto issue = [&](uint32_t tile) {
+        const uint32_t col0 = tile * C;
+        const uint32_t nvalid = min((uint32_t)C, (uint32_t)prm.ncols - col0);
+        mbar_arrive_expect_tx(bar, nvalid * (uint32_t)(L * sizeof(cpx<T>)));
+        for (uint32_t cc = 0; cc < nvalid; cc++)
+          bulk_load(inbuf + (size_t)cc * L, gin + (long long)(col0 + cc) * prm.in_stride_c, (uint32_t)(L * sizeof(cpx<T>)), bar);
+      };
+      if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+      }
+      __syncthreads();
+      uint32_t tile = blockIdx.x;
+      if (tid == 0 && tile < prm.ntiles) issue(tile);
+      uint32_t parity = 0;
+      for (; tile < prm.ntiles; tile += gridDim.x) {
+        Tile t = decode(prm, tile);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        {
+          const V* src = reinterpret_cast<const V*>(inbuf + (size_t)c_ld * L) + u_ld;
+#pragma unroll
+          for (int i = 0; i < P; i++) {
+            V v = src[i * TN];
+            x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
+          }
+        }
+        int c = c_ld, u = u_ld;
+        // stage 0 + first barrier, then the prefetch of the next tile, then the remaining stages
+        stage<0>(prm, x, smem + (size_t)c * PITCH, u);
+        __syncthreads();
+        if (tid == 0 && tile + gridDim.x < prm.ntiles) issue(tile + gridDim.x);
+        if constexpr (NST > 1) {
+          if constexpr (NST == 2) {
+            c = c_st;
+            u = u_st;
+          }
+          gather(x, smem + (size_t)c * PITCH, u);
+          if constexpr (NST > 2) __syncthreads();
+          run_stages<1>(prm, x, smem, c, u, c_st, u_st);
+        }
+        store(prm, t, c, u, x);
+        if (NST > 1) __syncthreads();
+      }
+    } else {
+      for (uint32_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+        Tile t = decode(prm, tile);
+        load(prm, t, c_ld, u_ld, x);
+        int c = c_ld, u = u_ld;
+        run_stages<0>(prm, x, smem, c, u, c_st, u_st);
+        if constexpr (DIT) {
+          dit_store(prm, t, c, u, x, smem);
+          __syncthreads();
+        } else if constexpr (PAIR) {
+          pair_dit_store(prm, t, c, u, x, smem);
+          __syncthreads();
+        } else {
+          store(prm, t, c, u, x);
+          if (NST > 1) __syncthreads();  // next tile's first scatter must not overtake this tile's gathers
+        }
+      }
     }
   }
 };

@@ -61,6 +61,21 @@ def test_real_fft_batched(comparand, n, batch):
         assert oracle.rel_l2(got[b], want) <= oracle.tolerance(n, np.float32)
 
 
+@pytest.mark.parametrize("n,batch,half", [(64, 3, True), (4096, 70000, True), (1 << 15, 5, False), (1 << 17, 3, True),
+                                          (1 << 17, 2, False), (1 << 20, 2, True)])
+def test_real_fft_unfused_split_path(comparand, monkeypatch, n, batch, half):
+    """The stand-alone split kernel (GENFFT_CUDA_FUSED_DIT=0) stays correct, incl. batch > 65535 grid rows."""
+    monkeypatch.setenv("GENFFT_CUDA_FUSED_DIT", "0")
+    x = np.random.default_rng(n).uniform(-1, 1, (batch, n)).astype(np.float32)
+    lim = n // 2 + 1 if half else n
+    plan = g.RealFFT(n, np.float32, half=half, batch=batch)
+    d_out = torch.empty((batch, lim), dtype=torch.complex64, device="cuda")
+    plan.forward(d_out, torch.from_numpy(x).cuda())
+    got = d_out.cpu().numpy()
+    for b in sorted({0, batch // 2, batch - 1}):
+        assert oracle.rel_l2(got[b], comparand.r2c(x[b], half)[:lim]) <= oracle.tolerance(n, np.float32)
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("in_place", [False, True])
 @pytest.mark.parametrize("lg", [1, 2, 3, 4, 6, 10, 14, 18, 20])

@@ -54,3 +54,6 @@ if __name__=="__main__":
         r2c(1<<22, 256)
     if "2d" in which:
         fft2d(4096,4096); fft2d(8192,8192); fft2d(32768,32768)
+    if "r2csmall" in which:
+        for n,b in ((4096, 1<<16), (32768, 1<<13)):
+            r2c(n,b)

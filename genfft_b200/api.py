@@ -177,6 +177,35 @@ class FFT(_Plan):
         return out
 
 
+    def transform_interleave(self, out, in1, in2):
+        """FFT<T>::transform_interleave(out, in1, in2) (fft.h:100-105): transform of in1 + i*in2; separate the two
+        real spectra with separate_2x_real_FFT."""
+        self._need()
+        o, i1 = _pair(out, in1, self.precision)
+        i2 = _Buf(in2)
+        if i2.cuda != o.cuda or i2.precision != self.precision:
+            raise ValueError("in2 must match in1")
+        self._check_len(o, self.out_dist)
+        self._check_len(i1, self.in_dist, complex_elems=False)
+        self._check_len(i2, self.in_dist, complex_elems=False)
+        if o.cuda:
+            check(lib().genfft_cuda_exec_c2c_interleave_dev(self._h, o.ptr, i1.ptr, i2.ptr, _stream()))
+        else:
+            check(lib().genfft_cuda_exec_c2c_interleave(self._h, o.ptr, i1.ptr, i2.ptr))
+        return out
+
+
+def separate_2x_real_FFT(out1, out2, inp, n: int):
+    """genfft::separate_2x_real_FFT(out1, out2, in, N) (FFTReal.h:35-66) on device tensors; out1/out2 may alias in."""
+    o1, o2, i = _Buf(out1, True), _Buf(out2, True), _Buf(inp)
+    if not (o1.cuda and o2.cuda and i.cuda):
+        raise ValueError("separate_2x_real_FFT works on device tensors (use the C++ mirror's host version otherwise)")
+    if min(o1.nscalars, o2.nscalars, i.nscalars) < 2 * n:
+        raise ValueError("buffers must hold n complex elements")
+    check(lib().genfft_cuda_separate_2x_real_dev(i.precision, o1.ptr, o2.ptr, i.ptr, n, _stream()))
+    return out1, out2
+
+
 class RealFFT(_Plan):
     """genfft::RealFFT<T> (FFTReal.h:186-221) plus a batch dimension; ``half`` is fixed per plan."""
 
@@ -303,6 +332,40 @@ class FFT2D(_Plan):
             check(lib().genfft_cuda_exec_c2c_2d_dev(self._h, o.ptr, out_stride, i.ptr, in_stride, int(inv), _stream()))
         else:
             check(lib().genfft_cuda_exec_c2c_2d(self._h, o.ptr, out_stride, i.ptr, in_stride, int(inv)))
+        return out
+
+
+class RealFFT2D(_Plan):
+    """genfft::RealFFT2D<T>(width, height) (FFTReal.h:71-184): forward transform of a real image to its full
+    width x height complex spectrum (the reference's inverse is a TODO, FFTReal.h:127-130)."""
+
+    def __init__(self, width: int | None = None, height: int | None = None, dtype=np.float32):
+        super().__init__()
+        if width is None:
+            return
+        self.precision = _precision(dtype)
+        check(lib().genfft_cuda_plan_r2c_2d(C.byref(self._h), self.precision, width, height))
+        self._w, self._hgt = width, height
+        self._n = width * height
+
+    def cols(self) -> int:
+        return self._w if self._h else 0
+
+    def rows(self) -> int:
+        return self._hgt if self._h else 0
+
+    def forward(self, out, inp, out_stride: int | None = None, in_stride: int | None = None):
+        """RealFFT2D<T>::forward(out, out_stride, in, in_stride); out_stride in complex elements, in_stride in scalars."""
+        self._need()
+        out_stride = self._w if out_stride is None else out_stride
+        in_stride = self._w if in_stride is None else in_stride
+        o, i = _pair(out, inp, self.precision)
+        if o.nscalars < 2 * ((self._hgt - 1) * out_stride + self._w) or i.nscalars < (self._hgt - 1) * in_stride + self._w:
+            raise ValueError("buffer too small for height x width with the given stride")
+        if o.cuda:
+            check(lib().genfft_cuda_exec_r2c_2d_dev(self._h, o.ptr, out_stride, i.ptr, in_stride, _stream()))
+        else:
+            check(lib().genfft_cuda_exec_r2c_2d(self._h, o.ptr, out_stride, i.ptr, in_stride))
         return out
 
 

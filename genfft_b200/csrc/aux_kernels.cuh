@@ -89,6 +89,74 @@ __global__ void __launch_bounds__(256) dit_kernel(const __grid_constant__ DitPar
   }
 }
 
+// separate_2x_real_FFT (include/genFFT/FFTReal.h:35-66): Fz is the N-point transform of x + i*y with x, y real;
+// recovers Fx and Fy.  Bins i and N-i are handled by one thread, so out1 or out2 may alias in.
+struct SeparateParams {
+  const void* in;
+  void* out1;
+  void* out2;
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) separate_kernel(const __grid_constant__ SeparateParams p) {
+  using V = typename vec2<T>::type;
+  const V* Fz = reinterpret_cast<const V*>(p.in);
+  V* Fx = reinterpret_cast<V*>(p.out1);
+  V* Fy = reinterpret_cast<V*>(p.out2);
+  const int N = p.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= N / 2; i += gridDim.x * blockDim.x) {
+    if (i == 0) {
+      V z = Fz[0], a, b;
+      a.x = z.x;
+      a.y = T(0);
+      b.x = z.y;
+      b.y = T(0);
+      Fx[0] = a;
+      Fy[0] = b;
+      continue;
+    }
+    const int k = N - i;
+    const V zi = Fz[i], zk = Fz[k];
+    V x, y, xc, yc;
+    x.x = (zi.x + zk.x) * T(0.5);
+    x.y = (zi.y - zk.y) * T(0.5);
+    y.x = (zk.y + zi.y) * T(0.5);
+    y.y = (zk.x - zi.x) * T(0.5);
+    xc.x = x.x;
+    xc.y = -x.y;
+    yc.x = y.x;
+    yc.y = -y.y;
+    Fx[i] = x;
+    Fy[i] = y;
+    Fx[k] = xc;
+    Fy[k] = yc;
+  }
+}
+
+// Hermitian completion of a real image's spectrum (RealFFT2D<T>::forward, include/genFFT/FFTReal.h:90-103):
+// out[(H-i)%H][j] = conj(out[i][W-j]) for W/2 < j < W.
+struct MirrorParams {
+  void* data;
+  long long stride;
+  int w, h;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) mirror2d_kernel(const __grid_constant__ MirrorParams p) {
+  using V = typename vec2<T>::type;
+  V* d = reinterpret_cast<V*>(p.data);
+  const int first = p.w / 2 + 1;
+  for (int i = blockIdx.y; i < p.h; i += gridDim.y) {
+    const int k = i ? p.h - i : 0;
+    for (int j = first + blockIdx.x * blockDim.x + threadIdx.x; j < p.w; j += gridDim.x * blockDim.x) {
+      V v = d[(long long)i * p.stride + (p.w - j)];
+      v.y = -v.y;
+      d[(long long)k * p.stride + j] = v;
+    }
+  }
+}
+
 // out[b*out_dist + r*out_stride + c] = in[b*in_dist + r*in_stride + c]  (complex elements)
 struct CopyParams {
   const void* in;

@@ -117,6 +117,49 @@ int genfft_cuda_exec_c2c_real_in(genfft_cuda_plan_t plan, void* out, const void*
   return exec_batched_host(p, out, in_real, es / 2, p->in_dist, p->n, es, p->out_dist, p->n, false, 0, false, true);
 }
 
+// FFT<T>::transform_interleave(out, in1, in2) (fft.h:100-105): host pointers
+int genfft_cuda_exec_c2c_interleave(genfft_cuda_plan_t plan, void* out, const void* in1, const void* in2) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (!out || !in1 || !in2) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (p->batch != 1) return set_error(GENFFT_CUDA_ERR_ARG, "transform_interleave on host pointers supports batch 1");
+  const size_t es = elem_size(p->precision);
+  const size_t rbytes = (size_t)p->n * es / 2, cbytes = (size_t)p->n * es;
+  int rc = ensure_stage(p, 2 * ((rbytes + 255) & ~(size_t)255), cbytes);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  char* d1 = (char*)p->stage_in;
+  char* d2 = d1 + ((rbytes + 255) & ~(size_t)255);
+  HX_TRY(cudaMemcpyAsync(d1, in1, rbytes, cudaMemcpyHostToDevice, st));
+  HX_TRY(cudaMemcpyAsync(d2, in2, rbytes, cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_c2c_interleave_dev(plan, p->stage_out, d1, d2, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpyAsync(out, p->stage_out, cbytes, cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
+// RealFFT2D<T>::forward(out, out_stride, in, in_stride) (FFTReal.h:83-104): host pointers
+int genfft_cuda_exec_r2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in, int64_t in_stride) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_R2C_2D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out_stride < p->width || in_stride < p->width) return set_error(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
+  const size_t es = elem_size(p->precision);
+  const size_t in_bytes = (size_t)p->width * p->height * es / 2, out_bytes = (size_t)p->width * p->height * es;
+  int rc = ensure_stage(p, in_bytes, out_bytes);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  HX_TRY(cudaMemcpy2DAsync(p->stage_in, p->width * es / 2, in, in_stride * es / 2, p->width * es / 2, p->height,
+                           cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_r2c_2d_dev(plan, p->stage_out, p->width, p->stage_in, p->width, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpy2DAsync(out, out_stride * es, p->stage_out, p->width * es, p->width * es, p->height,
+                           cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
 int genfft_cuda_exec_r2c(genfft_cuda_plan_t plan, void* out, const void* in) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_1d plan");

@@ -626,7 +626,7 @@ struct DitFuse {
 // runs `steps`; count = batch (1D) or rows (row passes of 2D); cols = columns for column passes
 static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, long long scratch_pitch,
                      size_t scratch_elems, long long count, long long cols, int inverse, cudaStream_t stream,
-                     const FinalStore* fs = nullptr, const DitFuse* df = nullptr) {
+                     const FinalStore* fs = nullptr, const DitFuse* df = nullptr, const void* in2 = nullptr) {
   std::vector<Step> steps(steps_in);
   if (fs && steps.size() > 1) steps.back().safe = false;  // the last pass writes elsewhere than it reads
   const size_t es = elem_size(plan->precision);
@@ -683,7 +683,8 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     PassParams p = st.col ? emit_col(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, cols, inverse, st.brev)
                           : emit_1d(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, count, inverse, st.brev);
     if (st.real_in) {
-      p.in_real = 1;
+      p.in_real = in2 ? 2 : 1;
+      p.in2 = in2;
       p.mode = M_GEN;
     }
     if (df && s == n - 1) {
@@ -736,6 +737,22 @@ static int new_plan(Plan** out, PlanKind kind, int precision) {
 }
 
 static const long long kMaxN = 1LL << 27;
+
+// sequence + twiddles of an n-point real transform (n/2-point packed complex transform + split)
+static int setup_r2c_tables(Plan* p, int precision, long long n) {
+  int rc = build_seq(&p->seq, p->device, precision, n >= 2 ? n / 2 : 1, false);
+  if (!rc) rc = two_level_table(p->device, precision, n >= 8 ? n : 8, &p->dit_hi, &p->dit_lo, &p->dit_shift);
+  if (!rc && n >= 4 && p->seq.passes.size() == 1)  // W_n^k, k < n/2, for the fused split
+    rc = twiddle_table(p->device, precision, n, 1, n / 2, &p->dit_full);
+  if (!rc && p->seq.passes.size() > 1) {
+    const PassSpec& last = p->seq.passes.back();
+    if (last.k->launch[M_COLTWDIT][0] && last.Ns % last.k->C == 0 && last.Ns * last.R == n / 2) {
+      rc = twiddle_table(p->device, precision, n, 1, last.Ns, &p->dit_a);
+      if (!rc) rc = twiddle_table(p->device, precision, 2 * last.R, 1, last.R, &p->dit_b);
+    }
+  }
+  return rc;
+}
 
 }  // namespace genfft_cuda
 
@@ -797,18 +814,7 @@ int genfft_cuda_plan_r2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
     delete p;
     return fail(GENFFT_CUDA_ERR_ARG, "in_dist must be even (the real input is read as packed complex pairs)");
   }
-  rc = build_seq(&p->seq, p->device, precision, n >= 2 ? n / 2 : 1, false);
-  if (!rc && n >= 8) rc = two_level_table(p->device, precision, n, &p->dit_hi, &p->dit_lo, &p->dit_shift);
-  if (!rc && n >= 4 && p->seq.passes.size() == 1)  // W_n^k, k < n/2, for the fused split
-    rc = twiddle_table(p->device, precision, n, 1, n / 2, &p->dit_full);
-  if (!rc && p->seq.passes.size() > 1) {
-    const PassSpec& last = p->seq.passes.back();
-    if (last.k->launch[M_COLTWDIT][0] && last.Ns % last.k->C == 0 && last.Ns * last.R == n / 2) {
-      rc = twiddle_table(p->device, precision, n, 1, last.Ns, &p->dit_a);
-      if (!rc) rc = twiddle_table(p->device, precision, 2 * last.R, 1, last.R, &p->dit_b);
-    }
-  }
-  if (!rc && n < 8) rc = two_level_table(p->device, precision, 8, &p->dit_hi, &p->dit_lo, &p->dit_shift);
+  rc = setup_r2c_tables(p, precision, n);
   if (rc) {
     delete p;
     return rc;
@@ -927,7 +933,7 @@ namespace genfft_cuda {
 int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
 
 int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStream_t stream, bool brev, bool real_in,
-                      long long batch) {
+                      long long batch, const void* in2) {
   if (!p || p->kind != PLAN_C2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (batch < 0) batch = p->batch;
@@ -942,27 +948,37 @@ int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStrea
     cp.in_stride = p->in_dist;
     cp.out_stride = p->out_dist;
     cp.in_real = real_in;
+    if (in2) return fail(GENFFT_CUDA_ERR_SIZE, "transform_interleave needs n >= 2");
     return launch_copy(p->precision, cp, 1, stream);
   }
   std::vector<Step> steps;
   seq_steps(p->seq, false, steps, brev, real_in);
   View vin{const_cast<void*>(in), p->in_dist}, vout{out, p->out_dist};
-  return run_chain(p, steps, vin, vout, p->n, (size_t)p->n * batch, batch, 0, inverse, stream);
+  return run_chain(p, steps, vin, vout, p->n, (size_t)p->n * batch, batch, 0, inverse, stream, nullptr, nullptr, in2);
 }
 
 int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t st, long long batch) {
-  if (!p || p->kind != PLAN_R2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c_1d plan");
+  return exec_r2c_strided(p, out, in, st, batch, 0, 0);
+}
+
+// in_dist (real scalars) / out_dist (complex elements) override the plan's when non-zero (rows of a real image)
+int exec_r2c_strided(Plan* pl, void* out, const void* in, cudaStream_t st, long long batch, long long in_dist_o,
+                     long long out_dist_o) {
+  if (!pl || (pl->kind != PLAN_R2C_1D && pl->kind != PLAN_R2C_2D)) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c plan");
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
-  if (batch < 0) batch = p->batch;
+  if (batch < 0) batch = pl->batch;
+  Plan* p = pl;
+  const long long P_IN = in_dist_o ? in_dist_o : pl->in_dist, P_OUT = out_dist_o ? out_dist_o : pl->out_dist;
+  if (pl->n >= 2 && (P_IN & 1)) return fail(GENFFT_CUDA_ERR_ARG, "real input distance must be even");
   const long long n = p->n;
   if (n <= 2) {  // no complex sub-transform: the split reads the input directly (FFTReal.h:206-207)
-    return launch_dit(p, out, p->out_dist, in, n == 1 ? p->in_dist : p->in_dist / 2, (int)n, p->half, batch, n == 1, st);
+    return launch_dit(p, out, P_OUT, in, n == 1 ? P_IN : P_IN / 2, (int)n, p->half, batch, n == 1, st);
   }
   // n/2 fits on chip: one kernel does the packed complex transform and the split (fused real-FFT post-process)
   if (p->seq.passes.size() == 1 && p->dit_full && p->seq.passes[0].k->launch[M_ROWDIT][0] &&
       env_int("GENFFT_CUDA_FUSED_DIT", 1) && out != in) {
     const PassSpec& ps = p->seq.passes[0];
-    PassParams pp = emit_1d(ps, n / 2, in, p->in_dist / 2, out, p->out_dist, batch, 0, false);
+    PassParams pp = emit_1d(ps, n / 2, in, P_IN / 2, out, P_OUT, batch, 0, false);
     pp.mode = M_ROWDIT;
     pp.dit_tw = p->dit_full;
     pp.dit_half = p->half;
@@ -970,7 +986,7 @@ int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t st, long 
   }
   std::vector<Step> steps;
   seq_steps(p->seq, false, steps, false, false);
-  View vin{const_cast<void*>(in), p->in_dist / 2}, vout{out, p->out_dist};
+  View vin{const_cast<void*>(in), P_IN / 2}, vout{out, P_OUT};
   // multi-pass: the split is fused into the last pass, which then works on pairs of column groups
   if (p->seq.passes.size() > 1 && p->dit_a && env_int("GENFFT_CUDA_FUSED_DIT", 1)) {
     DitFuse df;
@@ -981,7 +997,7 @@ int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t st, long 
   }
   int rc = run_chain(p, steps, vin, vout, n / 2, (size_t)(n / 2) * batch, batch, 0, 0, st);
   if (rc) return rc;
-  return launch_dit(p, out, p->out_dist, out, p->out_dist, (int)n, p->half, batch, false, st);
+  return launch_dit(p, out, P_OUT, out, P_OUT, (int)n, p->half, batch, false, st);
 }
 
 bool plan_needs_scratch(const Plan* p) {
@@ -992,16 +1008,106 @@ bool plan_needs_scratch(const Plan* p) {
 extern "C" {
 
 int genfft_cuda_exec_c2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, int inverse, void* stream) {
-  return exec_c2c_internal(plan, out, in, inverse, (cudaStream_t)stream, false, false, -1);
+  return exec_c2c_internal(plan, out, in, inverse, (cudaStream_t)stream, false, false, -1, nullptr);
 }
 
 int genfft_cuda_exec_c2c_no_scramble_dev(genfft_cuda_plan_t plan, void* inout, int inverse, void* stream) {
-  return exec_c2c_internal(plan, inout, inout, inverse, (cudaStream_t)stream, true, false, -1);
+  return exec_c2c_internal(plan, inout, inout, inverse, (cudaStream_t)stream, true, false, -1, nullptr);
 }
 
 int genfft_cuda_exec_c2c_real_in_dev(genfft_cuda_plan_t plan, void* out, const void* in_real, void* stream) {
   if (out == in_real) return fail(GENFFT_CUDA_ERR_ARG, "transform_real requires out != in");
-  return exec_c2c_internal(plan, out, in_real, 0, (cudaStream_t)stream, false, true, -1);
+  return exec_c2c_internal(plan, out, in_real, 0, (cudaStream_t)stream, false, true, -1, nullptr);
+}
+
+int genfft_cuda_exec_c2c_interleave_dev(genfft_cuda_plan_t plan, void* out, const void* in1, const void* in2,
+                                        void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (!out || !in1 || !in2) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in1 || out == in2) return fail(GENFFT_CUDA_ERR_ARG, "transform_interleave requires out != in");
+  return exec_c2c_internal(p, out, in1, 0, (cudaStream_t)stream, false, true, -1, in2);
+}
+
+int genfft_cuda_separate_2x_real_dev(int precision, void* out1, void* out2, const void* in, int64_t n, void* stream) {
+  if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return fail(GENFFT_CUDA_ERR_ARG, "bad precision");
+  if (!out1 || !out2 || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (n < 1 || n > kMaxN) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld", (long long)n);
+  SeparateParams sp;
+  sp.in = in;
+  sp.out1 = out1;
+  sp.out2 = out2;
+  sp.n = (int)n;
+  const unsigned grid = (unsigned)std::min<long long>((n / 2 + 1 + 255) / 256, 8192);
+  if (precision == GENFFT_CUDA_F32)
+    separate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(sp);
+  else
+    separate_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(sp);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_plan_r2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t width, int64_t height) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(width) || !is_pow2(height) || width > kMaxN || height > kMaxN || width < 2)
+    return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld x %lld", (long long)width, (long long)height);
+  Plan* p;
+  int rc = new_plan(&p, PLAN_R2C_2D, precision);
+  if (rc) return rc;
+  p->width = width;
+  p->height = height;
+  p->n = width;
+  p->batch = height;
+  p->half = 1;
+  p->in_dist = width;
+  p->out_dist = width;
+  rc = setup_r2c_tables(p, precision, width);
+  if (!rc) rc = build_seq(&p->seq_v, p->device, precision, height, true);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+// RealFFT2D<T>::forward (include/genFFT/FFTReal.h:83-104): real rows -> half spectra (the reference packs row pairs
+// into one complex transform and separates them, :144-165; here each row is a real transform with the split fused),
+// column transforms on the width/2+1 independent columns, Hermitian completion of the remaining columns.
+int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
+                                int64_t in_stride, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_R2C_2D) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "RealFFT2D::forward requires out != in");
+  if (out_stride < p->width || in_stride < p->width) return fail(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = exec_r2c_strided(p, out, in, st, p->height, in_stride, out_stride);
+  if (rc) return rc;
+  const long long vcols = p->width / 2 + 1;
+  if (!p->seq_v.passes.empty()) {
+    std::vector<Step> steps;
+    seq_steps(p->seq_v, true, steps, false, false);
+    View v{out, out_stride};
+    rc = run_chain(p, steps, v, v, vcols, (size_t)vcols * p->height, 0, vcols, 0, st);
+    if (rc) return rc;
+  }
+  if (p->width > 2) {
+    MirrorParams mp;
+    mp.data = out;
+    mp.stride = out_stride;
+    mp.w = (int)p->width;
+    mp.h = (int)p->height;
+    dim3 grid((unsigned)std::min<long long>((p->width / 2 + 255) / 256, 1024), (unsigned)std::min<long long>(p->height, 65535));
+    if (p->precision == GENFFT_CUDA_F32)
+      mirror2d_kernel<float><<<grid, 256, 0, st>>>(mp);
+    else
+      mirror2d_kernel<double><<<grid, 256, 0, st>>>(mp);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  return GENFFT_CUDA_OK;
 }
 
 int genfft_cuda_exec_r2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream) {

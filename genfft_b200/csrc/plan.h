@@ -9,7 +9,7 @@
 
 namespace genfft_cuda {
 
-enum PlanKind { PLAN_C2C_1D, PLAN_R2C_1D, PLAN_C2C_2D, PLAN_VERT, PLAN_DIT, PLAN_DIST_ROWS, PLAN_DIST_COLS };
+enum PlanKind { PLAN_C2C_1D, PLAN_R2C_1D, PLAN_C2C_2D, PLAN_VERT, PLAN_DIT, PLAN_DIST_ROWS, PLAN_DIST_COLS, PLAN_R2C_2D };
 
 // one Stockham pass of a length-N sequence: radix R = kernel length, Ns = product of earlier radices
 struct PassSpec {
@@ -71,8 +71,10 @@ namespace genfft_cuda {
 size_t elem_size(int precision);
 int set_error(int code, const char* msg);
 int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStream_t stream, bool brev, bool real_in,
-                      long long batch);
+                      long long batch, const void* in2 = nullptr);
 int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t stream, long long batch);
+int exec_r2c_strided(Plan* p, void* out, const void* in, cudaStream_t stream, long long batch, long long in_dist,
+                     long long out_dist);
 bool plan_needs_scratch(const Plan* p);
 
 }  // namespace genfft_cuda

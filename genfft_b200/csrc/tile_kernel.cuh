@@ -42,7 +42,9 @@ struct PassParams {
   int map_load, map_store;   // 0 = lanes across columns (A), 1 = lanes along the sequence (B)
   int mode;                  // host side only: which compiled addressing mode to launch (enum Mode)
   int inverse;               // conjugate on load and on store
-  int in_real;               // input is real scalars (imag = 0); FFT<T>::transform_real, fft.h:90-94
+  int in_real;               // 1: input is real scalars (imag = 0), FFT<T>::transform_real, fft.h:90-94
+                             // 2: real part from `in`, imaginary part from `in2`, transform_interleave, fft.h:100-105
+  const void* in2;
   // bit-reversed input (transform_no_scramble contract, fft.h:69-73 / 132-136):
   //   offset = brev(t1*g_t1 + col*g_c + idx*g_i, brev_bits) * brev_stride + t0*in_t0 + col*in_stride_c
   int brev_bits;
@@ -277,7 +279,9 @@ struct TileKernel {
         off = base + (long long)idx * prm.in_stride_i;
       }
       if (valid) {
-        if (prm.in_real) {
+        if (prm.in_real == 2) {
+          x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], reinterpret_cast<const T*>(prm.in2)[off]);
+        } else if (prm.in_real) {
           x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], T(0));
         } else {
           V v = reinterpret_cast<const V*>(prm.in)[off];

@@ -65,6 +65,9 @@ int genfft_cuda_plan_r2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
                             int64_t in_dist, int64_t out_dist);
 /* 2D complex width x height (row-major, width contiguous).  FFT2D<T>(width, height) (fft.h:198-245). */
 int genfft_cuda_plan_c2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t width, int64_t height);
+/* 2D real input width x height.  RealFFT2D<T>(width, height) (FFTReal.h:71-184); forward only, as in the reference
+ * (its inverse is assert(!"TODO"), FFTReal.h:127-130). */
+int genfft_cuda_plan_r2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t width, int64_t height);
 /* n-point FFT along axis 0 of an (n x cols) row-major array.  FFTVert<T> (fft.h:115-171). */
 int genfft_cuda_plan_vert(genfft_cuda_plan_t* plan, int precision, int64_t n);
 /* real-FFT split / post-process of size n.  DIT<T> (fft.h:173-196), adjust_DIT_impl
@@ -89,6 +92,15 @@ int genfft_cuda_exec_c2c_dev(genfft_cuda_plan_t plan, void* out, const void* in,
 int genfft_cuda_exec_c2c_no_scramble_dev(genfft_cuda_plan_t plan, void* inout, int inverse, void* stream);
 /* FFT<T>::transform_real(out, in) (fft.h:90-94): n real scalars -> n complex bins. */
 int genfft_cuda_exec_c2c_real_in_dev(genfft_cuda_plan_t plan, void* out, const void* in_real, void* stream);
+/* FFT<T>::transform_interleave(out, in1, in2) (fft.h:100-105): transform of in1 + i*in2 (two real signals). */
+int genfft_cuda_exec_c2c_interleave_dev(genfft_cuda_plan_t plan, void* out, const void* in1, const void* in2,
+                                        void* stream);
+/* separate_2x_real_FFT(out1, out2, in, N) (FFTReal.h:35-66); out1 or out2 may alias in. */
+int genfft_cuda_separate_2x_real_dev(int precision, void* out1, void* out2, const void* in, int64_t n, void* stream);
+/* RealFFT2D<T>::forward(out, out_stride, in, in_stride) (FFTReal.h:83-104): real width x height image -> full
+ * width x height complex spectrum; out_stride in complex elements, in_stride in real scalars; out != in. */
+int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
+                                int64_t in_stride, void* stream);
 /* RealFFT<T>::forward(out, in, half) (FFTReal.h:204-213); half is fixed at plan time.  `out` is also the
  * workspace and must hold n/2+1 (half) or n complex elements per transform. */
 int genfft_cuda_exec_r2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream);
@@ -111,6 +123,8 @@ int genfft_cuda_exec_c2c(genfft_cuda_plan_t plan, void* out, const void* in, int
 int genfft_cuda_exec_c2c_no_scramble(genfft_cuda_plan_t plan, void* inout, int inverse);
 int genfft_cuda_exec_c2c_real_in(genfft_cuda_plan_t plan, void* out, const void* in_real);
 int genfft_cuda_exec_r2c(genfft_cuda_plan_t plan, void* out, const void* in);
+int genfft_cuda_exec_c2c_interleave(genfft_cuda_plan_t plan, void* out, const void* in1, const void* in2);
+int genfft_cuda_exec_r2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in, int64_t in_stride);
 int genfft_cuda_exec_c2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
                             int64_t in_stride, int inverse);
 int genfft_cuda_exec_vert(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,

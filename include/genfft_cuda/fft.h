@@ -96,6 +96,12 @@ struct FFT {
     detail::check(genfft_cuda_exec_c2c_real_in(impl.get(), out, in));
   }
 
+  ///@brief Computes forward transform of interleaved real data (fft.h:100-105); separate the two spectra with
+  ///       separate_2x_real_FFT.
+  void transform_interleave(std::complex<T>* out, const T* in1, const T* in2) {
+    detail::check(genfft_cuda_exec_c2c_interleave(impl.get(), out, in1, in2));
+  }
+
   /// additions: device pointers, asynchronous on `stream` (a cudaStream_t)
   template <bool inv>
   void transform_dev(void* d_out, const void* d_in, void* stream = nullptr) {
@@ -232,6 +238,34 @@ void separate_2x_real_FFT(std::complex<T>* out1, std::complex<T>* out2, const st
     out2[k] = std::complex<T>(yr, -yi);
   }
 }
+
+///@brief 2D FFT of a real image (mirror of genfft::RealFFT2D<T>, FFTReal.h:71-184); forward only, as in the reference
+template <class T>
+class RealFFT2D {
+ public:
+  RealFFT2D() = default;
+  RealFFT2D(int width, int height) : w(width), h(height) {
+    genfft_cuda_plan_t p = nullptr;
+    detail::check(genfft_cuda_plan_r2c_2d(&p, detail::precision_of<T>::value, width, height));
+    impl = detail::own(p);
+  }
+
+  ///@param out_stride stride, in complex elements, of the output array
+  ///@param in_stride stride, in scalar elements, of the input array (FFTReal.h:83)
+  void forward(std::complex<T>* out, int out_stride, const T* in, int in_stride) {
+    detail::check(genfft_cuda_exec_r2c_2d(impl.get(), out, out_stride, in, in_stride));
+  }
+  void forward_dev(void* d_out, int out_stride, const void* d_in, int in_stride, void* stream = nullptr) {
+    detail::check(genfft_cuda_exec_r2c_2d_dev(impl.get(), d_out, out_stride, d_in, in_stride, stream));
+  }
+
+  int cols() const { return impl ? w : 0; }
+  int rows() const { return impl ? h : 0; }
+
+ private:
+  int w = 0, h = 0;
+  detail::plan_ptr impl;
+};
 
 ///@brief 1D FFT of real input (mirror of genfft::RealFFT<T>, FFTReal.h:186-221)
 template <class T>

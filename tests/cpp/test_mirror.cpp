@@ -179,9 +179,12 @@ void run_all() {
   dummy(a);
   for (int i = 0; i < n; i++) b[i] = a[(i * 7 + 3) % n];
   std::vector<std::complex<T>> z(n), fz(n), fa(n), fb(n);
-  for (int i = 0; i < n; i++) z[i] = std::complex<T>(a[i], b[i]);
   genfft::FFT<T> fft(n);
-  fft.template transform<false>(fz.data(), z.data());
+  fft.transform_interleave(fz.data(), a.data(), b.data());  // fft.h:100-105
+  for (int i = 0; i < n; i++) z[i] = std::complex<T>(a[i], b[i]);
+  std::vector<std::complex<T>> fz2(n);
+  fft.template transform<false>(fz2.data(), z.data());
+  for (int i = 0; i < n; i++) CHECK(std::abs(cd(fz[i]) - cd(fz2[i])) <= fft_eps<T>(n), "transform_interleave");
   genfft::separate_2x_real_FFT(fa.data(), fb.data(), fz.data(), n);
   std::vector<cd> ra(a.begin(), a.end()), rb(b.begin(), b.end());
   fft_rec(ra, false);
@@ -192,7 +195,32 @@ void run_all() {
   }
 }
 
+template <class T>
+void test_real_fft2d(int w, int h) {
+  genfft::RealFFT2D<T> fft(w, h);
+  std::vector<T> in((size_t)w * h);
+  dummy(in);
+  std::vector<std::complex<T>> out((size_t)w * h);
+  fft.forward(out.data(), w, in.data(), w);
+  std::vector<cd> ref(in.begin(), in.end());
+  for (int r = 0; r < h; r++) {
+    std::vector<cd> row(ref.begin() + (size_t)r * w, ref.begin() + (size_t)(r + 1) * w);
+    fft_rec(row, false);
+    std::copy(row.begin(), row.end(), ref.begin() + (size_t)r * w);
+  }
+  for (int c = 0; c < w; c++) {
+    std::vector<cd> col(h);
+    for (int r = 0; r < h; r++) col[r] = ref[(size_t)r * w + c];
+    fft_rec(col, false);
+    for (int r = 0; r < h; r++) ref[(size_t)r * w + c] = col[r];
+  }
+  const double eps = fft_eps<T>(w * h);
+  for (size_t i = 0; i < in.size(); i++) CHECK(std::abs(cd(out[i]) - ref[i]) <= eps * 1.5, "real 2d %dx%d i=%zu", w, h, i);
+}
+
 int main() {
+  test_real_fft2d<float>(64, 32);
+  test_real_fft2d<double>(16, 128);
   genfft::FFT<float> empty;
   CHECK(!(bool)empty && empty.size() == 0, "default-constructed plan must be empty");
   bool threw = false;

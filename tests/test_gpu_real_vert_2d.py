@@ -222,3 +222,47 @@ def test_c5_shape_2d_properties():
         plan.transform(f, r)
         plan.transform(b, f, inv=True)
         assert (b / (w * h) - r).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [2, 8, 256, 4096, 1 << 15])
+def test_transform_interleave_and_separate(comparand, dt, n):
+    """FFT::transform_interleave + separate_2x_real_FFT (fft.h:100-105, FFTReal.h:35-66): two real spectra from
+    one complex transform."""
+    rng = np.random.default_rng(n)
+    a, b = rng.uniform(-1, 1, n).astype(dt), rng.uniform(-1, 1, n).astype(dt)
+    want_a, want_b = comparand.two_real(a, b)
+    plan = g.FFT(n, dt)
+    z = torch.empty(n, dtype=TCPX[dt], device="cuda")
+    plan.transform_interleave(z, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    fa, fb = torch.empty_like(z), torch.empty_like(z)
+    g.separate_2x_real_FFT(fa, fb, z, n)
+    assert oracle.rel_l2(fa.cpu().numpy(), want_a) <= oracle.tolerance(n, dt)
+    assert oracle.rel_l2(fb.cpu().numpy(), want_b) <= oracle.tolerance(n, dt)
+    g.separate_2x_real_FFT(z, fb, z, n)  # out1 aliases in, as the reference allows
+    assert oracle.rel_l2(z.cpu().numpy(), want_a) <= oracle.tolerance(n, dt)
+    h_z = np.empty(n, dtype=CPX[dt])
+    plan.transform_interleave(h_z, a, b)  # host pointers
+    assert oracle.rel_l2(h_z, np.fft.fft(a.astype(np.float64) + 1j * b.astype(np.float64))) <= oracle.tolerance(n, dt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("w,h", [(2, 2), (4, 2), (8, 8), (64, 16), (16, 256), (1024, 64), (256, 4096), (8192, 8)])
+def test_real_fft2d_vs_reference(checkers, dt, w, h):
+    """RealFFT2D::forward (FFTReal.h:83-104): untested in the reference; pinned against the compiled reference
+    where present and against numpy's fft2 of the real image."""
+    x = np.random.default_rng(w + 7 * h).uniform(-1, 1, (h, w)).astype(dt)
+    plan = g.RealFFT2D(w, h, dt)
+    assert plan.cols() == w and plan.rows() == h
+    d_out = torch.full((h, w), FILL, dtype=TCPX[dt], device="cuda")
+    plan.forward(d_out, torch.from_numpy(x).cuda())
+    got = d_out.cpu().numpy()
+    assert oracle.rel_l2(got, np.fft.fft2(x.astype(np.float64))) <= oracle.tolerance(w * h, dt)
+    ref = checkers[0]
+    if ref is not None and w >= 4 and h >= 2:
+        assert oracle.rel_l2(got, ref.real_fft2d(x)) <= oracle.tolerance(w * h, dt)
+    h_out = np.empty((h, w + 3), dtype=CPX[dt])
+    xin = np.zeros((h, w + 2), dtype=dt)
+    xin[:, :w] = x
+    plan.forward(h_out, xin, out_stride=w + 3, in_stride=w + 2)  # host pointers, padded strides
+    assert oracle.rel_l2(h_out[:, :w], got) <= 1e-6

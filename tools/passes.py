@@ -1,7 +1,7 @@
 """Scratch: run each large config once (after one warm-up) so that an ncu launch list shows per-pass times."""
 import sys, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import genfft_b200 as g
 which = sys.argv[1:] or ["c3", "c4", "c5"]
 if "c3" in which:

@@ -1,7 +1,7 @@
 """Scratch timing harness (not the contract bench): times device-resident configs with CUDA events."""
 import sys, os, json
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import genfft_b200 as g
 
 def time_it(fn, iters=20, warm=5):

@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--size", type=int, default=32768)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chunks", type=str, default="1,4")
+    ap.add_argument("--fracs", type=str, default="0.7:0.3")
+    ap.add_argument("--transports", type=str, default="nccl,p2p")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -35,9 +38,20 @@ def main():
     slab = torch.view_as_complex(torch.rand((hl, w, 2), generator=gen, device="cuda") * 2 - 1)
     flop = 5.0 * w * h * math.log2(w * h)
     sent = (w * h * 8 / world) * (world - 1) / world
-    for transport in ("nccl", "p2p"):
+    variants = []
+    for transport in args.transports.split(","):
         for transposed in (True, False):
-            plan = DistFFT2D(w, h, np.float32, transport=transport, transposed_out=transposed)
+            if transport == "nccl":
+                variants.append((transport, transposed, 1, 1.0, 1.0))
+            else:
+                for ch in [int(c) for c in args.chunks.split(",")]:
+                    for fr in (args.fracs.split(",") if ch > 1 else ["1:1"]):
+                        fl, frm = [float(v) for v in fr.split(":")]
+                        variants.append((transport, transposed, ch, fl, frm))
+    for transport, transposed, chunks, fl, frm in variants:
+        if True:
+            plan = DistFFT2D(w, h, np.float32, transport=transport, transposed_out=transposed, chunks=chunks,
+                             frac_local=fl, frac_remote=frm)
             for _ in range(args.warmup):
                 plan.transform(slab)
             dist.barrier()
@@ -56,6 +70,7 @@ def main():
             if rank == 0:
                 print(json.dumps({
                     "workload": f"C5: 2D C2C fp32 {w}x{h}, slab-decomposed over {world} GPUs", "transport": transport,
+                    "chunks": chunks, "frac_local": fl, "frac_remote": frm,
                     "output": "transposed (1 global transpose)" if transposed else "natural order (2 global transposes)",
                     "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
                     "alltoall_bytes_sent_per_gpu_per_transpose": sent,

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "genfft_cuda_plan_vert": (C.c_int, [_plan_p, C.c_int, _i64]),
     "genfft_cuda_plan_dit": (C.c_int, [_plan_p, C.c_int, _i64]),
     "genfft_cuda_plan_destroy": (C.c_int, [_vp]),
+    "genfft_cuda_plan_set_grid_fraction": (C.c_int, [_vp, C.c_double, C.c_double]),
     "genfft_cuda_plan_size": (_i64, [_vp]),
     "genfft_cuda_plan_num_passes": (C.c_int, [_vp]),
     "genfft_cuda_plan_scratch_bytes": (C.c_size_t, [_vp]),

@@ -508,6 +508,7 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
   int rc = kernel_occupancy(ps.k, ps.k->func[mode][inv], ps.k->smem_mode[mode], plan->device, &occ);
   if (rc) return rc;
   long long cap = (long long)plan->num_sms * occ;
+  if (p.grid_frac > 0.f && p.grid_frac < 1.f) cap = std::max<long long>(1, (long long)(cap * p.grid_frac));
   int grid = (int)std::min<long long>(p.ntiles, cap);
   ps.k->launch[mode][inv](p, grid, stream);
   g_launches++;
@@ -687,6 +688,7 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
       p.in2 = in2;
       p.mode = M_GEN;
     }
+    p.grid_frac = (s == n - 1) ? plan->grid_frac[1] : plan->grid_frac[0];
     if (df && s == n - 1) {
       // pair tiles: Ns/C tiles of {p} U {Ns-p} plus one tile for column 0
       p.mode = M_COLTWDIT;
@@ -873,6 +875,18 @@ int genfft_cuda_plan_dit(genfft_cuda_plan_t* plan, int precision, int64_t n) {
     return rc;
   }
   *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+// Launch only a fraction of the resident-CTA capacity for the passes of this plan (frac_other: all passes but the
+// last; frac_last: the last pass), so that kernels of two plans running on different streams share the SMs --
+// used to overlap a link-bound remote-store pass with the HBM-bound local pass of the next chunk.
+int genfft_cuda_plan_set_grid_fraction(genfft_cuda_plan_t plan, double frac_other, double frac_last) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!(frac_other > 0 && frac_other <= 1 && frac_last > 0 && frac_last <= 1))
+    return fail(GENFFT_CUDA_ERR_ARG, "fractions must be in (0, 1]");
+  plan->grid_frac[0] = (float)frac_other;
+  plan->grid_frac[1] = (float)frac_last;
   return GENFFT_CUDA_OK;
 }
 

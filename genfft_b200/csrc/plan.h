@@ -38,6 +38,7 @@ struct Plan {
   int half = 0;
   long long width = 0, height = 0;
   int nparts = 1;
+  float grid_frac[2] = {1.f, 1.f};  // share of the resident-CTA capacity: {all passes but the last, last pass}
   Seq seq;    // 1D sequence (c2c_1d: n; r2c: n/2; 2d: rows (width); vert: n)
   Seq seq_v;  // 2D: columns (height)
   // DIT twiddles (W_n two-level)

@@ -41,6 +41,7 @@ struct PassParams {
   int ncols;                 // valid columns along t2*C + c (tail tiles are masked)
   int map_load, map_store;   // 0 = lanes across columns (A), 1 = lanes along the sequence (B)
   int mode;                  // host side only: which compiled addressing mode to launch (enum Mode)
+  float grid_frac;           // host side only: fraction of the resident-CTA capacity to launch (0 = all)
   int inverse;               // conjugate on load and on store
   int in_real;               // 1: input is real scalars (imag = 0), FFT<T>::transform_real, fft.h:90-94
                              // 2: real part from `in`, imaginary part from `in2`, transform_interleave, fft.h:100-105

@@ -52,26 +52,60 @@ def _is_pow2(n: int) -> bool:
 
 
 class CudaSlabEngine:
-    """Local passes of the slab decomposition on the GPU (libgenfft_cuda dist_rows / dist_cols plans)."""
+    """Local passes of the slab decomposition on the GPU (libgenfft_cuda dist_rows / dist_cols plans).
 
-    def __init__(self, width: int, height: int, world: int, dtype):
+    With ``chunks > 1`` the slab is cut into row (column) chunks that alternate between two streams, each with its
+    own plan (own scratch) launched on a fraction of the SMs, so that the NVLink-bound remote-store pass of chunk k
+    overlaps the HBM-bound local pass of chunk k+1."""
+
+    def __init__(self, width: int, height: int, world: int, dtype, chunks: int = 1, frac_local: float = 0.7,
+                 frac_remote: float = 0.3):
         from .api import _precision
         self.w, self.h, self.p = width, height, world
         self.hl, self.wp = height // world, width // world
         self.precision = _precision(dtype)
         self.cdtype = torch.complex64 if self.precision == _lib.F32 else torch.complex128
+        self.esize = 8 if self.precision == _lib.F32 else 16
         self._rows = C.c_void_p()
         self._cols = C.c_void_p()
         check(lib().genfft_cuda_plan_dist_rows(C.byref(self._rows), self.precision, width, self.hl, world))
         check(lib().genfft_cuda_plan_dist_cols(C.byref(self._cols), self.precision, height, self.wp, world))
+        while chunks > 1 and (self.hl % chunks or self.wp % chunks or self.wp // chunks < 32):
+            chunks //= 2
+        self.chunks = max(1, chunks)
+        self._chunk_plans = []
+        if self.chunks > 1:
+            self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            for _ in range(2):
+                r, c = C.c_void_p(), C.c_void_p()
+                check(lib().genfft_cuda_plan_dist_rows(C.byref(r), self.precision, width, self.hl // self.chunks, world))
+                check(lib().genfft_cuda_plan_dist_cols(C.byref(c), self.precision, height, self.wp // self.chunks, world))
+                for h in (r, c):
+                    check(lib().genfft_cuda_plan_set_grid_fraction(h, frac_local, frac_remote))
+                self._chunk_plans.append((r, c))
 
     def __del__(self):
         try:
-            for h in (self._rows, self._cols):
+            for h in [self._rows, self._cols] + [x for pair in self._chunk_plans for x in pair]:
                 if h:
                     lib().genfft_cuda_plan_destroy(h)
         except Exception:
             pass
+
+    def _fan_out(self, launch):
+        """Runs launch(k, plan_pair) for every chunk on alternating side streams, fenced against the current stream."""
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        for s in self.streams:
+            s.wait_event(start)
+        for k in range(self.chunks):
+            with torch.cuda.stream(self.streams[k % 2]):
+                launch(k, self._chunk_plans[k % 2])
+        for s in self.streams:
+            done = torch.cuda.Event()
+            done.record(s)
+            main.wait_event(done)
 
     @staticmethod
     def _stream():
@@ -99,13 +133,32 @@ class CudaSlabEngine:
     # -- p2p transport: the store is the all-to-all -------------------------------------------------
     def rows_to_peers(self, slab, peer_ptrs, rank: int, inv: bool):
         arr = (C.c_void_p * self.p)(*peer_ptrs)
-        check(lib().genfft_cuda_exec_dist_rows_dev(self._rows, None, arr, 0, rank * self.hl, slab.data_ptr(), self.w,
-                                                   int(inv), self._stream()))
+        if self.chunks == 1:
+            check(lib().genfft_cuda_exec_dist_rows_dev(self._rows, None, arr, 0, rank * self.hl, slab.data_ptr(),
+                                                       self.w, int(inv), self._stream()))
+            return
+        rk = self.hl // self.chunks
+        base = slab.data_ptr()
+
+        def launch(k, plans):
+            check(lib().genfft_cuda_exec_dist_rows_dev(plans[0], None, arr, 0, rank * self.hl + k * rk,
+                                                       base + k * rk * self.w * self.esize, self.w, int(inv),
+                                                       self._stream()))
+        self._fan_out(launch)
 
     def cols_to_peers(self, block_ptr: int, peer_ptrs, rank: int, inv: bool):
         arr = (C.c_void_p * self.p)(*peer_ptrs)
-        check(lib().genfft_cuda_exec_dist_cols_dev(self._cols, None, arr, self.w, rank * self.wp, block_ptr, self.wp,
-                                                   int(inv), self._stream()))
+        if self.chunks == 1:
+            check(lib().genfft_cuda_exec_dist_cols_dev(self._cols, None, arr, self.w, rank * self.wp, block_ptr,
+                                                       self.wp, int(inv), self._stream()))
+            return
+        ck = self.wp // self.chunks
+
+        def launch(k, plans):
+            check(lib().genfft_cuda_exec_dist_cols_dev(plans[1], None, arr, self.w, rank * self.wp + k * ck,
+                                                       block_ptr + k * ck * self.esize, self.wp, int(inv),
+                                                       self._stream()))
+        self._fan_out(launch)
 
     def cols_ptr(self, out, block_ptr: int, inv: bool):
         check(lib().genfft_cuda_exec_dist_cols_dev(self._cols, out.data_ptr(), None, self.wp, 0, block_ptr, self.wp,
@@ -169,7 +222,8 @@ class DistFFT2D:
     """
 
     def __init__(self, width: int, height: int, dtype=np.float32, group=None, transport: str = "p2p",
-                 transposed_out: bool = False, engine=None):
+                 transposed_out: bool = False, engine=None, chunks: int = 1, frac_local: float = 0.7,
+                 frac_remote: float = 0.3):
         if dist is None or not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.group = group
@@ -185,7 +239,8 @@ class DistFFT2D:
         self.hl, self.wp = height // self.world, width // self.world
         self.transport = transport
         self.transposed_out = transposed_out
-        self.engine = engine if engine is not None else CudaSlabEngine(width, height, self.world, dtype)
+        self.engine = engine if engine is not None else CudaSlabEngine(
+            width, height, self.world, dtype, chunks if transport == "p2p" else 1, frac_local, frac_remote)
         e = self.engine
         if transport == "nccl":
             self.send = e.empty(self.world, self.hl, self.wp)

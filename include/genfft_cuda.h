@@ -74,6 +74,10 @@ int genfft_cuda_plan_vert(genfft_cuda_plan_t* plan, int precision, int64_t n);
  * (include/genFFT/generic/fft_dit_impl_generic.inl:27-61). */
 int genfft_cuda_plan_dit(genfft_cuda_plan_t* plan, int precision, int64_t n);
 int genfft_cuda_plan_destroy(genfft_cuda_plan_t plan);
+/* Launch only a fraction of the resident-CTA capacity (frac_other: every pass but the last; frac_last: the last
+ * pass) so that two plans on different streams share the SMs -- used to overlap an NVLink-bound remote-store pass
+ * with the HBM-bound local pass of the next chunk in the distributed 2D transform. */
+int genfft_cuda_plan_set_grid_fraction(genfft_cuda_plan_t plan, double frac_other, double frac_last);
 
 /* introspection (used by the benchmark to compute roofline figures) */
 int64_t genfft_cuda_plan_size(genfft_cuda_plan_t plan);          /* FFT<T>::size(), fft.h:107 */

@@ -31,9 +31,11 @@ def main():
         want_i = np.fft.ifft2(full.astype(np.complex128)) * (w * h)
         tol = (1e-6 if dt == np.float32 else 1e-14) * np.log2(w * h)
         slab = torch.from_numpy(full[rank * hl:(rank + 1) * hl].copy()).cuda()
-        for transport in ("nccl", "p2p"):
+        for transport, chunks in (("nccl", 1), ("p2p", 1), ("p2p", 4)):
             for transposed in (False, True):
-                plan = DistFFT2D(w, h, dt, transport=transport, transposed_out=transposed)
+                if chunks > 1 and (w // world) // chunks < 32:
+                    continue
+                plan = DistFFT2D(w, h, dt, transport=transport, transposed_out=transposed, chunks=chunks)
                 for inv, want in ((False, want_f), (True, want_i)):
                     for rep in range(2):  # twice: buffers are reused between calls
                         got = plan.transform(slab, inv)
@@ -44,7 +46,7 @@ def main():
                     ok = err <= tol
                     fails += not ok
                     if rank == 0 or not ok:
-                        print(f"[rank {rank}] {w}x{h} {dt.__name__} {transport} transposed={transposed} inv={inv}: "
+                        print(f"[rank {rank}] {w}x{h} {dt.__name__} {transport} chunks={chunks} transposed={transposed} inv={inv}: "
                               f"rel-L2 {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
                 dist.barrier()
                 plan.close()

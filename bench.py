@@ -56,50 +56,59 @@ def measured_peaks() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled from a
+    background thread (the timed region is milliseconds long, shorter than nvidia-smi's sampling period)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[int, int]] = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        clk = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((int(clk), int(rs)))
+                    except Exception as e:  # keep the bench alive
+                        self.err = repr(e)
+                        return
+                    time.sleep(0.0005)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as e:
+            self.err = repr(e)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": [f"unavailable: {self.err}"]}
+        clocks = sorted(c for c, _ in self.samples)
+        seen = set()
+        for _, rs in self.samples:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    seen.add(name)
+        return {"sm_mhz": float(clocks[len(clocks) // 2]), "sm_max_mhz": self.max_mhz, "samples": len(clocks),
+                "reasons": sorted(seen)}
 
 
 def reference_arm(args, rank: int, world: int) -> int:
@@ -252,7 +261,7 @@ def main() -> int:
                 "d2h_bytes_per_step": N_FFT * BATCH * 8, "ms_per_step": e2e_s * 1e3,
                 "api": "genfft_cuda_exec_c2c (host pointers, pinned; chunked H2D/compute/D2H overlap on two streams)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fft_tile_kernel<float,4096,16,1,M_ROW,false>",
+                     "traffic": traffic, "kernel": "fft_tile_kernel<float,4096,16,1,M_ROWTMA,false> (cp.async.bulk prefetch)",
                      "kernel_ms": kernel_ms, "algorithmic_bytes": ALGO_BYTES_PER_STEP, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "plan": plan.describe(),
@@ -270,7 +279,8 @@ def main() -> int:
             t_one = ref.bench_c2c(N_FFT, 2048, 1)
             line["cpu_baseline"] = {
                 "value": 5.0 * N_FFT * 12 * count / t_cpu / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
-                "sample": f"{count} of {BATCH} transforms, fresh U(-1,1) input per transform, {threads} threads "
+                "sample": f"{count} transforms ({count / BATCH:.1f} x the {BATCH}-transform batch, ~10 s of CPU work), "
+                          f"fresh U(-1,1) input per transform, {threads} threads "
                           f"(restated fft_bench.cpp FFT_1D loop, forward only); {ref.describe()}",
                 "single_core_value": 5.0 * N_FFT * 12 * 2048 / t_one / 1e9,
             }

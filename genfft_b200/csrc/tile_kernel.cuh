@@ -42,6 +42,7 @@ struct PassParams {
   int map_load, map_store;   // 0 = lanes across columns (A), 1 = lanes along the sequence (B)
   int mode;                  // host side only: which compiled addressing mode to launch (enum Mode)
   float grid_frac;           // host side only: fraction of the resident-CTA capacity to launch (0 = all)
+  uint32_t tiles_per_cta;    // 0: grid-stride loop over tiles (persistent grid); K > 0: CTA b owns tiles [b*K, b*K+K)
   int inverse;               // conjugate on load and on store
   int in_real;               // 1: input is real scalars (imag = 0), FFT<T>::transform_real, fft.h:90-94
                              // 2: real part from `in`, imaginary part from `in2`, transform_interleave, fft.h:100-105
@@ -96,9 +97,15 @@ __host__ __device__ constexpr int stage_tw_offset(int L, int P, int s) {
 }
 __host__ __device__ constexpr int stage_tw_size(int L, int P) { return stage_tw_offset(L, P, num_stages(L, P)); }
 
-// one padding element per 16: conflict-free for the stride-r scatters of every radix <= 16
-__host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 4); }
-__host__ __device__ constexpr int tile_pitch(int L) { return pad_idx(L) | 1; }
+// Shared-memory padding: one element per 2^PADSH.  A 128-byte wavefront covers 16 float2 or 8 double2 elements; the
+// radix-P scatter of the first stage has element stride P, which one pad element per 16 makes conflict-free for
+// P = 16 (stride 17) in both precisions, while radix-8 on double2 needs one per 8 (stride 9).
+template <typename T, int P>
+constexpr int pad_shift() { return (sizeof(T) == 8 && P == 8) ? 3 : 4; }
+template <int PADSH>
+__host__ __device__ constexpr int pad_idx_t(int i) { return i + (i >> PADSH); }
+template <int PADSH>
+__host__ __device__ constexpr int tile_pitch_t(int L) { return pad_idx_t<PADSH>(L) | 1; }
 
 // Addressing modes.  M_GEN handles everything at run time (bit-reversed / real input, split and peer
 // stores, any mapping); the others are the hot paths with the addressing resolved at compile time so
@@ -150,7 +157,10 @@ struct TileKernel {
   static constexpr int TN = L / P;
   static constexpr int THREADS = TN * C;
   static constexpr int NST = num_stages(L, P);
-  static constexpr int PITCH = tile_pitch(L);
+  static constexpr int PADSH = pad_shift<T, P>();
+  static constexpr int PADN = 1 << PADSH;
+  static constexpr int PITCH = tile_pitch_t<PADSH>(L);
+  static __host__ __device__ constexpr int pad_idx(int i) { return pad_idx_t<PADSH>(i); }
   static constexpr bool TMA = MODE == M_ROWTMA;
   static constexpr bool DIT = MODE == M_ROWDIT;
   static constexpr bool PAIR = MODE == M_COLTWDIT;
@@ -378,8 +388,8 @@ struct TileKernel {
         for (int s = 0; s < R; s++) x[m + RegDFT<R>::out_bin(s) * M] = y[s];
       } else {
         const int base = (j - p) * R + p;
-        if constexpr (NS >= 16 || NS == 1) {
-          // pad_idx(base + b*NS) == pad_idx(base) + b*(NS + NS/16): immediate offsets from one address
+        if constexpr (NS >= PADN || NS == 1) {
+          // pad_idx(base + b*NS) == pad_idx(base) + b*(NS + NS/PADN): immediate offsets from one address
           V* dst = reinterpret_cast<V*>(sm) + pad_idx(base);
 #pragma unroll
           for (int s = 0; s < R; s++) {
@@ -387,7 +397,7 @@ struct TileKernel {
             V v;
             v.x = y[s].x;
             v.y = y[s].y;
-            dst[NS == 1 ? b : b * (NS + NS / 16)] = v;
+            dst[NS == 1 ? b : b * (NS + NS / PADN)] = v;
           }
         } else {
 #pragma unroll
@@ -404,11 +414,11 @@ struct TileKernel {
   }
 
   static __device__ __forceinline__ void gather(cpx<T> (&x)[P], const cpx<T>* sm, int u) {
-    if constexpr (TN >= 16) {
+    if constexpr (TN >= PADN) {
       const V* src = reinterpret_cast<const V*>(sm) + pad_idx(u);
 #pragma unroll
       for (int i = 0; i < P; i++) {
-        V v = src[i * (TN + TN / 16)];
+        V v = src[i * (TN + TN / PADN)];
         x[i] = cpx<T>(v.x, v.y);
       }
     } else {
@@ -577,10 +587,13 @@ struct TileKernel {
         fence_barrier_init();
       }
       __syncthreads();
-      uint32_t tile = blockIdx.x;
-      if (tid == 0 && tile < prm.ntiles) issue(tile);
+      const uint32_t K = prm.tiles_per_cta;
+      const uint32_t step = K ? 1u : gridDim.x;
+      const uint32_t tile_end = K ? min(prm.ntiles, (blockIdx.x + 1u) * K) : prm.ntiles;
+      uint32_t tile = K ? blockIdx.x * K : blockIdx.x;
+      if (tid == 0 && tile < tile_end) issue(tile);
       uint32_t parity = 0;
-      for (; tile < prm.ntiles; tile += gridDim.x) {
+      for (; tile < tile_end; tile += step) {
         Tile t = decode(prm, tile);
         mbar_wait(bar, parity);
         parity ^= 1;
@@ -596,7 +609,7 @@ struct TileKernel {
         // stage 0 + first barrier, then the prefetch of the next tile, then the remaining stages
         stage<0>(prm, x, smem + (size_t)c * PITCH, u);
         __syncthreads();
-        if (tid == 0 && tile + gridDim.x < prm.ntiles) issue(tile + gridDim.x);
+        if (tid == 0 && tile + step < tile_end) issue(tile + step);
         if constexpr (NST > 1) {
           if constexpr (NST == 2) {
             c = c_st;
@@ -610,7 +623,10 @@ struct TileKernel {
         if (NST > 1) __syncthreads();
       }
     } else {
-      for (uint32_t tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+      const uint32_t K = prm.tiles_per_cta;
+      const uint32_t step = K ? 1u : gridDim.x;
+      const uint32_t tile_end = K ? min(prm.ntiles, (blockIdx.x + 1u) * K) : prm.ntiles;
+      for (uint32_t tile = K ? blockIdx.x * K : blockIdx.x; tile < tile_end; tile += step) {
         Tile t = decode(prm, tile);
         load(prm, t, c_ld, u_ld, x);
         int c = c_ld, u = u_ld;

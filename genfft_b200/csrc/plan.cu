@@ -103,7 +103,8 @@ static std::vector<KernelEntry>& registry(int precision) {
 // points-per-thread variant where several are compiled (default 16).
 static const KernelEntry* find_kernel(int precision, long long L, bool wide) {
   const bool f32 = precision == GENFFT_CUDA_F32;
-  const int cap = wide ? env_int(f32 ? "GENFFT_CUDA_WIDE_C_F32" : "GENFFT_CUDA_WIDE_C_F64", 1 << 30) : 1 << 30;
+  // 128-byte row segments (16 float2 / 8 double2 columns) measured best with one-shot grids (tools/sweep.sh)
+  const int cap = wide ? env_int(f32 ? "GENFFT_CUDA_WIDE_C_F32" : "GENFFT_CUDA_WIDE_C_F64", f32 ? 16 : 8) : 1 << 30;
   const int want_p = wide ? env_int(f32 ? "GENFFT_CUDA_P_F32" : "GENFFT_CUDA_P_F64", 16) : 16;
   const KernelEntry* best = nullptr;
   for (int pass = 0; pass < 2 && !best; pass++) {

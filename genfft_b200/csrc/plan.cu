@@ -98,23 +98,31 @@ static std::vector<KernelEntry>& registry(int precision) {
   return precision == GENFFT_CUDA_F32 ? f32 : f64;
 }
 
-// wide = prefer the largest C (column passes), else the smallest (contiguous batched).
-// Tuning knobs: GENFFT_CUDA_WIDE_C_{F32,F64} caps C of wide kernels, GENFFT_CUDA_P_{F32,F64} picks the
-// points-per-thread variant where several are compiled (default 16).
+// Kernel shape for a length-L pass.  Narrow (contiguous batched) use takes the fewest sequences per CTA.  Wide (column)
+// use wants row segments of at least 128 bytes and CTAs of ~256 threads in float / ~128 in double (128 registers per
+// thread there): measured best with one-shot grids (tools/sweep.sh).  Tuning knobs: GENFFT_CUDA_WIDE_C_{F32,F64}
+// forces the column count, GENFFT_CUDA_P_{F32,F64} picks the points-per-thread variant where several are compiled.
 static const KernelEntry* find_kernel(int precision, long long L, bool wide) {
   const bool f32 = precision == GENFFT_CUDA_F32;
-  // 128-byte row segments (16 float2 / 8 double2 columns) measured best with one-shot grids (tools/sweep.sh)
-  const int cap = wide ? env_int(f32 ? "GENFFT_CUDA_WIDE_C_F32" : "GENFFT_CUDA_WIDE_C_F64", f32 ? 16 : 8) : 1 << 30;
   const int want_p = wide ? env_int(f32 ? "GENFFT_CUDA_P_F32" : "GENFFT_CUDA_P_F64", 16) : 16;
+  const int forced = wide ? env_int(f32 ? "GENFFT_CUDA_WIDE_C_F32" : "GENFFT_CUDA_WIDE_C_F64", 0) : 0;
+  const long long min_seg = f32 ? 16 : 8, target_threads = f32 ? 256 : 128;
+  const long long desired = forced ? forced : std::max(min_seg, target_threads * 16 / std::max(16LL, L));
   const KernelEntry* best = nullptr;
+  auto dist = [&](const KernelEntry& e) { return std::abs(ilog2(e.C) - ilog2(desired)); };
   for (int pass = 0; pass < 2 && !best; pass++) {
     for (auto& e : registry(precision)) {
       if (e.L != L) continue;
       if (wide && !e.launch[M_COL][0]) continue;
       if (!wide && !e.launch[M_ROW][0]) continue;
-      if (pass == 0 && (e.P != want_p && L >= 16)) continue;   // preferred P first
-      if (pass == 0 && wide && e.C > cap) continue;
-      if (!best || (wide ? e.C > best->C : e.C < best->C)) best = &e;
+      if (pass == 0 && (e.P != want_p && L >= 16)) continue;  // preferred P first
+      if (!best) {
+        best = &e;
+      } else if (!wide) {
+        if (e.C < best->C) best = &e;
+      } else if (dist(e) < dist(*best) || (dist(e) == dist(*best) && e.C > best->C)) {
+        best = &e;
+      }
     }
   }
   return best;
@@ -309,7 +317,7 @@ static long long max_single_len(int precision, bool wide) {
 }
 static long long max_pass_len(int precision) {
   return env_int(precision == GENFFT_CUDA_F32 ? "GENFFT_CUDA_MAXLEN_F32" : "GENFFT_CUDA_MAXLEN_F64",
-                 precision == GENFFT_CUDA_F32 ? 2048 : 2048);
+                 512);  // small tiles + one more pass beat 1-CTA-per-SM tiles once grids are one-shot (tools/sweep.sh)
 }
 
 static int build_seq(Seq* seq, int device, int precision, long long N, bool wide) {

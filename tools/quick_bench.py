@@ -57,3 +57,5 @@ if __name__=="__main__":
     if "r2csmall" in which:
         for n,b in ((4096, 1<<16), (32768, 1<<13)):
             r2c(n,b)
+    if "2dmid" in which:
+        fft2d(4096, 512); fft2d(4096, 1024); fft2d(4096, 2048); fft2d(1024, 1024); fft2d(2048, 2048)

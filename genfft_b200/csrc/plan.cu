@@ -692,55 +692,105 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     if (rc) return rc;
     cur = stage;
   }
+  // ---- assign the buffers of every step ----
+  struct StepIO {
+    View src, dst;
+    bool src_scr, dst_scr;
+  };
+  std::vector<StepIO> io(n);
   bool dst_is_out = (toggles % 2 == 0);
+  bool cur_scr = false;
   for (size_t s = 0; s < n; s++) {
     const Step& st = steps[s];
     View dst;
+    bool d_scr;
     if (s == 0) {
       dst = dst_is_out ? out : scr;
+      d_scr = !dst_is_out;
     } else if (st.safe) {
       dst = cur;  // in place
+      d_scr = cur_scr;
     } else {
       dst_is_out = !dst_is_out;
       dst = dst_is_out ? out : scr;
+      d_scr = !dst_is_out;
     }
-    PassParams p = st.col ? emit_col(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, cols, inverse, st.brev)
-                          : emit_1d(*st.ps, st.N, cur.ptr, cur.pitch, dst.ptr, dst.pitch, count, inverse, st.brev);
-    if (st.real_in) {
-      p.in_real = in2 ? 2 : 1;
-      p.in2 = in2;
-      p.mode = M_GEN;
-    }
-    p.grid_frac = (s == n - 1) ? plan->grid_frac[1] : plan->grid_frac[0];
-    if (df && s == n - 1) {
-      // pair tiles: Ns/C tiles of {p} U {Ns-p} plus one tile for column 0
-      p.mode = M_COLTWDIT;
-      p.n2 = (uint32_t)(st.ps->Ns / st.ps->k->C) + 1u;
-      p.ntiles = (uint32_t)(count * p.n2);
-      p.dit_half = df->half;
-      p.dit_a = df->dit_a;
-      p.dit_tw = df->dit_tw;
-    }
-    if (fs && s == n - 1) {
-      p.mode = M_GEN;
-      const long long Ns = (st.N == st.ps->R) ? 1 : st.ps->Ns;
-      const int sh = fs->part_log2 - ilog2(Ns);
-      if (sh < 0) return fail(GENFFT_CUDA_ERR_SIZE, "part size 2^%d smaller than pass stride %lld", fs->part_log2, Ns);
-      p.out_split_log2 = sh;
-      if (fs->peers) {
-        p.use_peers = 1;
-        for (int g = 0; g < fs->npeers && g < kMaxPeers; g++)
-          p.out_peer[g] = (char*)fs->peers[g] + fs->peer_offset * (long long)es;
-      } else {
-        p.out_stride_khi = fs->part_stride;
-      }
-    }
-    int rc = launch_pass(plan, *st.ps, p, stream);
-    if (rc) return rc;
+    io[s] = StepIO{cur, dst, cur_scr, d_scr};
     cur = dst;
+    cur_scr = d_scr;
   }
   if (cur.ptr != out.ptr) return fail(GENFFT_CUDA_ERR_ARG, "internal: pass chain did not end in the output buffer");
-  (void)es;
+
+  // ---- execute.  Consecutive passes along the same dimension form a segment.  Experimental knob
+  // GENFFT_CUDA_L2_GROUP_MB > 0 runs a segment's independent units (sequences of a batch, rows, columns) in groups of
+  // that size, all passes of a group back to back, hoping to read the intermediate back from the 126 MB L2 instead
+  // of HBM.  Measured on B200 it LOSES (C5 10.7 -> 13.4 ms at 64 MiB groups, 19.7 ms at 16 MiB; C4 4.9 -> 6.3 ms):
+  // the per-group kernels are single-wave and launch/latency-bound, so it is off by default. ----
+  const long long l2_group_bytes = (long long)env_int("GENFFT_CUDA_L2_GROUP_MB", 0) << 20;
+  size_t seg_begin = 0;
+  while (seg_begin < n) {
+    size_t seg_end = seg_begin + 1;
+    while (seg_end < n && steps[seg_end].col == steps[seg_begin].col) seg_end++;
+    const bool col = steps[seg_begin].col;
+    const long long units = col ? cols : count;
+    const long long unit_bytes = steps[seg_begin].N * (long long)es;
+    long long group = units;
+    if (seg_end - seg_begin >= 2 && l2_group_bytes > 0 && !copy_in) {
+      group = std::max<long long>(1, l2_group_bytes / unit_bytes);
+      if (col) {  // whole column tiles
+        int cmax = 1;
+        for (size_t s = seg_begin; s < seg_end; s++) cmax = std::max(cmax, steps[s].ps->k->C);
+        group = std::max<long long>(cmax, group / cmax * cmax);
+      }
+      group = std::min(group, units);
+    }
+    for (long long g0 = 0; g0 < units; g0 += group) {
+      const long long gn = std::min(group, units - g0);
+      for (size_t s = seg_begin; s < seg_end; s++) {
+        const Step& st = steps[s];
+        const size_t src_es = st.real_in ? es / 2 : es;
+        // element offset of the group inside a buffer: sequences are `pitch` apart, columns are adjacent
+        auto off = [&](const View& v) { return col ? g0 : g0 * v.pitch; };
+        const char* src = (const char*)io[s].src.ptr + (size_t)off(io[s].src) * src_es;
+        char* dst = (char*)io[s].dst.ptr + (size_t)off(io[s].dst) * es;
+        const bool peers_out = fs && fs->peers && s == n - 1;
+        PassParams p = st.col ? emit_col(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev)
+                              : emit_1d(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev);
+        if (st.real_in) {
+          p.in_real = in2 ? 2 : 1;
+          p.in2 = in2 ? (const char*)in2 + (size_t)off(io[s].src) * src_es : nullptr;
+          p.mode = M_GEN;
+        }
+        p.grid_frac = (s == n - 1) ? plan->grid_frac[1] : plan->grid_frac[0];
+        if (df && s == n - 1) {
+          // pair tiles: Ns/C tiles of {p} U {Ns-p} plus one tile for column 0
+          p.mode = M_COLTWDIT;
+          p.n2 = (uint32_t)(st.ps->Ns / st.ps->k->C) + 1u;
+          p.ntiles = (uint32_t)(gn * p.n2);
+          p.dit_half = df->half;
+          p.dit_a = df->dit_a;
+          p.dit_tw = df->dit_tw;
+        }
+        if (fs && s == n - 1) {
+          p.mode = M_GEN;
+          const long long Ns = (st.N == st.ps->R) ? 1 : st.ps->Ns;
+          const int sh = fs->part_log2 - ilog2(Ns);
+          if (sh < 0) return fail(GENFFT_CUDA_ERR_SIZE, "part size 2^%d smaller than pass stride %lld", fs->part_log2, Ns);
+          p.out_split_log2 = sh;
+          if (fs->peers) {
+            p.use_peers = 1;
+            for (int g = 0; g < fs->npeers && g < kMaxPeers; g++)
+              p.out_peer[g] = (char*)fs->peers[g] + (size_t)(fs->peer_offset + off(io[s].dst)) * es;
+          } else {
+            p.out_stride_khi = fs->part_stride;
+          }
+        }
+        int rc = launch_pass(plan, *st.ps, p, stream);
+        if (rc) return rc;
+      }
+    }
+    seg_begin = seg_end;
+  }
   return GENFFT_CUDA_OK;
 }
 

@@ -314,12 +314,35 @@ def extras(g, np, torch) -> dict:
 
     peak, _ = measured_peaks()
     try:
-        # C1: single N=1024 fp32 forward+inverse (latency)
+        # C1: single N=1024 fp32 forward+inverse (latency): through the Python mirror, through raw pointers, and as
+        # one CUDA graph of the two launches
         p = g.FFT(1024, np.float32)
         x = torch.randn(1024, dtype=torch.complex64, device="cuda")
         y, z = torch.empty_like(x), torch.empty_like(x)
         ms = timed(lambda: (p.forward(y, x), p.inverse(z, y)), iters=200, warm=20)
-        out["C1_1d_c2c_f32_n1024_fwd_inv"] = {"us_per_pair": ms * 1e3, "gflops": 2 * 5 * 1024 * 10 / (ms * 1e-3) / 1e9}
+        c1 = {"us_per_pair": ms * 1e3, "gflops": 2 * 5 * 1024 * 10 / (ms * 1e-3) / 1e9}
+        lib, h, st = g.lib(), p._h, torch.cuda.current_stream().cuda_stream
+        px, py, pz = x.data_ptr(), y.data_ptr(), z.data_ptr()
+        ms = timed(lambda: (lib.genfft_cuda_exec_c2c_dev(h, py, px, 0, st), lib.genfft_cuda_exec_c2c_dev(h, pz, py, 1, st)),
+                   iters=500, warm=50)
+        c1["us_per_pair_c_abi_raw_pointers"] = ms * 1e3
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                p.forward(y, x)
+                p.inverse(z, y)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                p.forward(y, x)
+                p.inverse(z, y)
+            ms = timed(graph.replay, iters=500, warm=50)
+            c1["us_per_pair_cuda_graph"] = ms * 1e3
+            assert float((z / 1024 - x).abs().max()) < 1e-4
+        except Exception as e:
+            c1["cuda_graph_error"] = repr(e)
+        out["C1_1d_c2c_f32_n1024_fwd_inv"] = c1
         # C3: N=2^24 fp64
         n = 1 << 24
         p = g.FFT(n, np.float64)

@@ -212,6 +212,12 @@ class PeerBuffers:
             lib().genfft_cuda_free(self.local)
             self.local = None
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class DistFFT2D:
     """Slab-decomposed genfft::FFT2D<T>(width, height) (fft.h:198-245) over a process group.

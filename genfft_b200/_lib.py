@@ -39,6 +39,9 @@ _SIGNATURES = {
     "genfft_cuda_plan_c2c_1d": (C.c_int, [_plan_p, C.c_int, _i64, _i64, _i64, _i64]),
     "genfft_cuda_plan_r2c_1d": (C.c_int, [_plan_p, C.c_int, _i64, _i64, C.c_int, _i64, _i64]),
     "genfft_cuda_plan_c2c_2d": (C.c_int, [_plan_p, C.c_int, _i64, _i64]),
+    "genfft_cuda_plan_c2r_1d": (C.c_int, [_plan_p, C.c_int, _i64, _i64, _i64, _i64]),
+    "genfft_cuda_exec_c2r_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "genfft_cuda_exec_c2r": (C.c_int, [_vp, _vp, _vp]),
     "genfft_cuda_plan_vert": (C.c_int, [_plan_p, C.c_int, _i64]),
     "genfft_cuda_plan_dit": (C.c_int, [_plan_p, C.c_int, _i64]),
     "genfft_cuda_plan_destroy": (C.c_int, [_vp]),

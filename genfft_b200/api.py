@@ -240,6 +240,35 @@ class RealFFT(_Plan):
         return out
 
 
+class InverseRealFFT(_Plan):
+    """Half-spectrum inverse of RealFFT (an addition: the reference has none, README.txt:51-52).  ``inverse(out, inp)``
+    maps n/2+1 bins to n real points, unscaled like every genFFT inverse: inverse(forward(x)) == n * x."""
+
+    def __init__(self, n: int | None = None, dtype=np.float32, batch: int = 1, in_dist: int = 0, out_dist: int = 0):
+        super().__init__()
+        if n is None:
+            return
+        self.precision = _precision(dtype)
+        self.batch = batch
+        self.in_dist = in_dist or n // 2 + 1
+        self.out_dist = out_dist or n
+        check(lib().genfft_cuda_plan_c2r_1d(C.byref(self._h), self.precision, n, batch, in_dist, out_dist))
+        self._n = n
+
+    def inverse(self, out, inp):
+        self._need()
+        o, i = _pair(out, inp, self.precision)
+        if i.nscalars < 2 * ((self.batch - 1) * self.in_dist + self._n // 2 + 1):
+            raise ValueError("input buffer too small")
+        if o.nscalars < (self.batch - 1) * self.out_dist + self._n:
+            raise ValueError("output buffer too small")
+        if o.cuda:
+            check(lib().genfft_cuda_exec_c2r_dev(self._h, o.ptr, i.ptr, _stream()))
+        else:
+            check(lib().genfft_cuda_exec_c2r(self._h, o.ptr, i.ptr))
+        return out
+
+
 class FFTVert(_Plan):
     """genfft::FFTVert<T> (fft.h:115-171): n-point FFT along axis 0 of an (n x cols) array."""
 

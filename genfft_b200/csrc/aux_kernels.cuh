@@ -157,6 +157,44 @@ __global__ void __launch_bounds__(256) mirror2d_kernel(const __grid_constant__ M
   }
 }
 
+// Half-spectrum inverse of a real transform (not in the reference: README.txt:51-52 "Maybe").  Pre-process of the
+// N/2+1 bins X into the N/2-point packed spectrum Z' = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) conj(W_N^k),
+// M = N/2, whose unscaled inverse complex transform is N * (x[2m] + i x[2m+1]).
+struct C2rParams {
+  const void* in;
+  void* out;
+  long long in_dist, out_dist;  // complex elements
+  int n;
+  int batch;
+  const void* tw_hi;
+  const void* tw_lo;
+  int tw_shift;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) c2r_pre_kernel(const __grid_constant__ C2rParams p) {
+  using V = typename vec2<T>::type;
+  const int M = p.n >> 1;
+  for (long long b = blockIdx.y; b < p.batch; b += gridDim.y) {
+    const V* X = reinterpret_cast<const V*>(p.in) + b * p.in_dist;
+    V* Z = reinterpret_cast<V*>(p.out) + b * p.out_dist;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x) {
+      const V xk = X[k], xm = X[M - k];
+      const T ax = xk.x + xm.x, ay = xk.y - xm.y;
+      const T dx = xk.x - xm.x, dy = xk.y + xm.y;
+      const uint32_t e = (uint32_t)k;
+      V wh = __ldg(reinterpret_cast<const V*>(p.tw_hi) + (e >> p.tw_shift));
+      V wl = __ldg(reinterpret_cast<const V*>(p.tw_lo) + (e & ((1u << p.tw_shift) - 1u)));
+      const cpx<T> w = cmul(cpx<T>(wh.x, wh.y), cpx<T>(wl.x, wl.y));  // W_N^k
+      const T tx = dx * w.x + dy * w.y, ty = dy * w.x - dx * w.y;    // d * conj(w)
+      V z;
+      z.x = ax - ty;
+      z.y = ay + tx;
+      Z[k] = z;
+    }
+  }
+}
+
 // out[b*out_dist + r*out_stride + c] = in[b*in_dist + r*in_stride + c]  (complex elements)
 struct CopyParams {
   const void* in;

@@ -160,6 +160,25 @@ int genfft_cuda_exec_r2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stri
   return GENFFT_CUDA_OK;
 }
 
+// half-spectrum inverse on host pointers
+int genfft_cuda_exec_c2r(genfft_cuda_plan_t plan, void* out, const void* in) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2R_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2r_1d plan");
+  if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  const size_t es = elem_size(p->precision);
+  const size_t in_bytes = ((size_t)(p->batch - 1) * p->in_dist + p->n / 2 + 1) * es;
+  const size_t out_bytes = ((size_t)(p->batch - 1) * p->out_dist + p->n) * es / 2;
+  int rc = ensure_stage(p, in_bytes, out_bytes);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  HX_TRY(cudaMemcpyAsync(p->stage_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_c2r_dev(plan, p->stage_out, p->stage_in, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpyAsync(out, p->stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
 int genfft_cuda_exec_r2c(genfft_cuda_plan_t plan, void* out, const void* in) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_1d plan");

@@ -967,6 +967,7 @@ int genfft_cuda_plan_destroy(genfft_cuda_plan_t plan) {
   if (!plan) return GENFFT_CUDA_OK;
   Plan* p = plan;
   if (p->scratch) cudaFree(p->scratch);
+  if (p->aux) cudaFree(p->aux);
   if (p->stage_in) cudaFree(p->stage_in);
   if (p->stage_out) cudaFree(p->stage_out);
   if (p->streams_ready) {
@@ -1195,6 +1196,93 @@ int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_
     CU_TRY(cudaGetLastError());
   }
   return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_plan_c2r_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, int64_t batch, int64_t in_dist,
+                            int64_t out_dist) {
+  if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
+  if (!is_pow2(n) || n < 2 || n > 2 * kMaxN)
+    return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld (power of two >= 2 required)", (long long)n);
+  if (batch < 1) return fail(GENFFT_CUDA_ERR_ARG, "batch must be >= 1");
+  Plan* p;
+  int rc = new_plan(&p, PLAN_C2R_1D, precision);
+  if (rc) return rc;
+  p->n = n;
+  p->batch = batch;
+  p->half = 1;
+  p->in_dist = in_dist ? in_dist : n / 2 + 1;
+  p->out_dist = out_dist ? out_dist : n;
+  if (n >= 2 && (p->out_dist & 1)) {
+    delete p;
+    return fail(GENFFT_CUDA_ERR_ARG, "out_dist must be even (the real output is written as packed complex pairs)");
+  }
+  rc = build_seq(&p->seq, p->device, precision, n / 2, false);
+  if (!rc) rc = two_level_table(p->device, precision, n, &p->dit_hi, &p->dit_lo, &p->dit_shift);  // W_n^k, exact n
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *plan = static_cast<genfft_cuda_plan_t>(p);
+  return GENFFT_CUDA_OK;
+}
+
+// Unscaled inverse of RealFFT<T>::forward(half = true): out[j] = n * x[j].  `in` holds n/2+1 bins per transform.
+int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_C2R_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2r_1d plan");
+  if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "c2r requires out != in");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = p->n, M = n / 2;
+  const size_t es = elem_size(p->precision);
+  // stage the pre-processed spectrum Z' (M complex per transform) in plan-owned memory
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    const size_t need = (size_t)M * p->batch * es;
+    if (p->aux_bytes < need) {
+      if (p->aux) {
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaFree(p->aux));
+        p->aux = nullptr;
+        p->aux_bytes = 0;
+      }
+      if (cudaMalloc(&p->aux, need) != cudaSuccess) return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc(%zu) failed", need);
+      p->aux_bytes = need;
+    }
+  }
+  C2rParams cp;
+  memset(&cp, 0, sizeof cp);
+  cp.in = in;
+  cp.out = p->aux;
+  cp.in_dist = p->in_dist;
+  cp.out_dist = M;
+  cp.n = (int)n;
+  cp.batch = (int)p->batch;
+  cp.tw_hi = p->dit_hi;
+  cp.tw_lo = p->dit_lo;
+  cp.tw_shift = p->dit_shift;
+  dim3 grid((unsigned)std::min<long long>((M + 255) / 256, 4096), (unsigned)std::min<long long>(p->batch, 65535));
+  if (p->precision == GENFFT_CUDA_F32)
+    c2r_pre_kernel<float><<<grid, 256, 0, st>>>(cp);
+  else
+    c2r_pre_kernel<double><<<grid, 256, 0, st>>>(cp);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  if (p->seq.passes.empty()) {  // M == 1: the inverse transform is the identity
+    CopyParams c2;
+    memset(&c2, 0, sizeof c2);
+    c2.in = p->aux;
+    c2.out = out;
+    c2.rows = p->batch;
+    c2.cols = 1;
+    c2.in_stride = 1;
+    c2.out_stride = p->out_dist / 2;
+    return launch_copy(p->precision, c2, 1, st);
+  }
+  std::vector<Step> steps;
+  seq_steps(p->seq, false, steps, false, false);
+  View vin{p->aux, M}, vout{out, p->out_dist / 2};
+  return run_chain(p, steps, vin, vout, M, (size_t)M * p->batch, p->batch, 0, 1, st);
 }
 
 int genfft_cuda_exec_r2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream) {

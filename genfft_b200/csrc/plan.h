@@ -9,7 +9,7 @@
 
 namespace genfft_cuda {
 
-enum PlanKind { PLAN_C2C_1D, PLAN_R2C_1D, PLAN_C2C_2D, PLAN_VERT, PLAN_DIT, PLAN_DIST_ROWS, PLAN_DIST_COLS, PLAN_R2C_2D };
+enum PlanKind { PLAN_C2C_1D, PLAN_R2C_1D, PLAN_C2C_2D, PLAN_VERT, PLAN_DIT, PLAN_DIST_ROWS, PLAN_DIST_COLS, PLAN_R2C_2D, PLAN_C2R_1D };
 
 // one Stockham pass of a length-N sequence: radix R = kernel length, Ns = product of earlier radices
 struct PassSpec {
@@ -53,6 +53,8 @@ struct Plan {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   size_t scratch_need = 0;  // upper bound known at plan time (0 if none / depends on exec args)
+  void* aux = nullptr;  // device staging owned by device-pointer entry points (c2r pre-processed spectrum)
+  size_t aux_bytes = 0;
   // host-pointer staging
   void* stage_in = nullptr;
   void* stage_out = nullptr;

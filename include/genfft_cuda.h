@@ -63,6 +63,11 @@ int genfft_cuda_plan_c2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
  * in_dist in real scalars (0 = n), out_dist in complex elements (0 = n/2+1 if half else n). */
 int genfft_cuda_plan_r2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, int64_t batch, int half,
                             int64_t in_dist, int64_t out_dist);
+/* Half-spectrum INVERSE of the real transform: n/2+1 bins -> n real points, unscaled (out = n * x).  An addition:
+ * the reference has no inverse real FFT (README.txt:51-52).  in_dist in complex elements (0 = n/2+1), out_dist in
+ * real scalars (0 = n). */
+int genfft_cuda_plan_c2r_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, int64_t batch, int64_t in_dist,
+                            int64_t out_dist);
 /* 2D complex width x height (row-major, width contiguous).  FFT2D<T>(width, height) (fft.h:198-245). */
 int genfft_cuda_plan_c2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t width, int64_t height);
 /* 2D real input width x height.  RealFFT2D<T>(width, height) (FFTReal.h:71-184); forward only, as in the reference
@@ -105,6 +110,8 @@ int genfft_cuda_separate_2x_real_dev(int precision, void* out1, void* out2, cons
  * width x height complex spectrum; out_stride in complex elements, in_stride in real scalars; out != in. */
 int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
                                 int64_t in_stride, void* stream);
+/* inverse of RealFFT<T>::forward(half = true), unscaled; out != in; n >= 2. */
+int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream);
 /* RealFFT<T>::forward(out, in, half) (FFTReal.h:204-213); half is fixed at plan time.  `out` is also the
  * workspace and must hold n/2+1 (half) or n complex elements per transform. */
 int genfft_cuda_exec_r2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream);
@@ -127,6 +134,7 @@ int genfft_cuda_exec_c2c(genfft_cuda_plan_t plan, void* out, const void* in, int
 int genfft_cuda_exec_c2c_no_scramble(genfft_cuda_plan_t plan, void* inout, int inverse);
 int genfft_cuda_exec_c2c_real_in(genfft_cuda_plan_t plan, void* out, const void* in_real);
 int genfft_cuda_exec_r2c(genfft_cuda_plan_t plan, void* out, const void* in);
+int genfft_cuda_exec_c2r(genfft_cuda_plan_t plan, void* out, const void* in);
 int genfft_cuda_exec_c2c_interleave(genfft_cuda_plan_t plan, void* out, const void* in1, const void* in2);
 int genfft_cuda_exec_r2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in, int64_t in_stride);
 int genfft_cuda_exec_c2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,

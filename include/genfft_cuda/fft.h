@@ -284,9 +284,20 @@ struct RealFFT {
     detail::check(genfft_cuda_exec_r2c_dev(plan(half), d_out, d_in, stream));
   }
 
+  /// addition (the reference has no inverse real FFT, README.txt:51-52): n/2+1 bins -> n real points, unscaled
+  void inverse(T* out, const std::complex<T>* in) {
+    if (!inv_impl) {
+      genfft_cuda_plan_t raw = nullptr;
+      detail::check(genfft_cuda_plan_c2r_1d(&raw, detail::precision_of<T>::value, n, 1, 0, 0));
+      inv_impl = detail::own(raw);
+    }
+    detail::check(genfft_cuda_exec_c2r(inv_impl.get(), out, in));
+  }
+
   int size() const noexcept { return n; }
 
  private:
+  detail::plan_ptr inv_impl;
   genfft_cuda_plan_t plan(bool half) {
     detail::plan_ptr& p = impl[half ? 1 : 0];
     if (!p) {

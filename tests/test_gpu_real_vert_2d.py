@@ -266,3 +266,29 @@ def test_real_fft2d_vs_reference(checkers, dt, w, h):
     xin[:, :w] = x
     plan.forward(h_out, xin, out_stride=w + 3, in_stride=w + 2)  # host pointers, padded strides
     assert oracle.rel_l2(h_out[:, :w], got) <= 1e-6
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,batch", [(2, 3), (4, 1), (8, 2), (64, 5), (4096, 3), (1 << 15, 2), (1 << 17, 2), (1 << 20, 1)])
+def test_half_spectrum_inverse(dt, n, batch):
+    """The inverse real FFT (absent in the reference): inverse(forward(x)) == n * x, and agreement with numpy's
+    irfft on an arbitrary Hermitian half spectrum."""
+    rng = np.random.default_rng(n + batch)
+    x = rng.uniform(-1, 1, (batch, n)).astype(dt)
+    fwd = g.RealFFT(n, dt, half=True, batch=batch)
+    inv = g.InverseRealFFT(n, dt, batch=batch)
+    spec = torch.empty((batch, n // 2 + 1), dtype=TCPX[dt], device="cuda")
+    fwd.forward(spec, torch.from_numpy(x).cuda())
+    back = torch.empty((batch, n), dtype=torch.float32 if dt == np.float32 else torch.float64, device="cuda")
+    inv.inverse(back, spec)
+    eps = (1e-5 + n * 1e-8) if dt == np.float32 else (1e-8 + n * 1e-12)
+    assert np.max(np.abs(back.cpu().numpy() / n - x)) <= eps
+    s = (rng.uniform(-1, 1, (batch, n // 2 + 1)) + 1j * rng.uniform(-1, 1, (batch, n // 2 + 1))).astype(CPX[dt])
+    s[:, 0] = s[:, 0].real
+    s[:, -1] = s[:, -1].real
+    want = np.fft.irfft(s.astype(np.complex128), n=n, axis=1) * n
+    inv.inverse(back, torch.from_numpy(s).cuda())
+    assert oracle.rel_l2(back.cpu().numpy(), want) <= oracle.tolerance(n, dt)
+    h_out = np.empty((batch, n), dtype=dt)
+    inv.inverse(h_out, s)  # host pointers
+    assert oracle.rel_l2(h_out, want) <= oracle.tolerance(n, dt)

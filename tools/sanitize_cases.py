@@ -1,0 +1,30 @@
+"""Scratch: one small launch of every kernel mode, for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import genfft_b200 as g
+for dt, cd in ((np.float32, torch.complex64), (np.float64, torch.complex128)):
+    rd = torch.float32 if dt == np.float32 else torch.float64
+    # M_ROW / M_ROWTMA (needs >= 4 tiles per SM)
+    for n, b in ((4096, 3), (1024, 2400), (4096, 600), (64, 7), (8192, 2)):
+        x = torch.randn(b, n, dtype=cd, device="cuda"); y = torch.empty_like(x)
+        p = g.FFT(n, dt, batch=b); p.forward(y, x); p.inverse(x, y)
+    # M_FIRST / M_COLTW (2 and 3 passes), M_GEN (no_scramble, real input)
+    for n in (1 << 15, 1 << 19):
+        x = torch.randn(2, n, dtype=cd, device="cuda"); y = torch.empty_like(x)
+        p = g.FFT(n, dt, batch=2); p.forward(y, x); p.inverse(x, y)
+    x = torch.randn(1 << 15, dtype=cd, device="cuda"); g.FFT(1 << 15, dt).transform_no_scramble(x)
+    r = torch.randn(4096, dtype=rd, device="cuda"); y = torch.empty(4096, dtype=cd, device="cuda"); g.FFT(4096, dt).transform_real(y, r)
+    # M_ROWDIT, M_COLTWDIT, stand-alone split, c2r
+    for n, b in ((4096, 5), (1 << 17, 2), (1 << 19, 1)):
+        r = torch.randn(b, n, dtype=rd, device="cuda"); y = torch.empty(b, n // 2 + 1, dtype=cd, device="cuda")
+        g.RealFFT(n, dt, half=True, batch=b).forward(y, r)
+        g.InverseRealFFT(n, dt, batch=b).inverse(r, y)
+        y2 = torch.empty(b, n, dtype=cd, device="cuda"); g.RealFFT(n, dt, half=False, batch=b).forward(y2, r)
+    # M_COL (vert), 2D, RealFFT2D
+    x = torch.randn(256, 37, dtype=cd, device="cuda"); y = torch.empty_like(x); g.FFTVert(256, dt).transform(y, x, 37)
+    x = torch.randn(8192, 40, dtype=cd, device="cuda"); y = torch.empty_like(x); g.FFTVert(8192, dt).transform(y, x, 40)
+    x = torch.randn(512, 1024, dtype=cd, device="cuda"); y = torch.empty_like(x); g.FFT2D(1024, 512, dt).transform(y, x)
+    r = torch.randn(64, 256, dtype=rd, device="cuda"); y = torch.empty(64, 256, dtype=cd, device="cuda"); g.RealFFT2D(256, 64, dt).forward(y, r)
+torch.cuda.synchronize()
+print("cases done")

@@ -525,6 +525,15 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
   if (frac) cap = std::max<long long>(1, (long long)(cap * p.grid_frac));
   const bool persistent = frac || env_int("GENFFT_CUDA_PERSISTENT", 0);
   PassParams q = p;
+  // Experimental (off): TMA staging of column tiles, one cp.async.bulk per 128-256-byte row.  Measured on B200 it
+  // LOSES badly (C3 294 -> 484 us, C5 10.7 -> 18.4 ms): the bulk-copy engine is not made for hundreds of tiny copies
+  // per tile; a tiled tensor map (cp.async.bulk.tensor, one instruction per tile) is the form to try next.
+  if ((mode == M_COL || mode == M_COLTW || mode == M_FIRST) && env_int("GENFFT_CUDA_TMA_COLS", 0)) {
+    const long long es = (long long)elem_size(plan->precision);
+    const bool aligned = ((uintptr_t)p.in % 16 == 0) && (p.in_stride_c == 1) && ((p.in_stride_i * es) % 16 == 0) &&
+                         ((p.in_t0 * es) % 16 == 0) && ((p.in_t1 * es) % 16 == 0) && ((ps.k->C * es) % 16 == 0);
+    q.tma_cols = (aligned && p.ncols % ps.k->C == 0 && num_stages(ps.k->L, ps.k->P) > 1) ? 1 : 0;
+  }
   int grid;
   if (persistent) {
     q.tiles_per_cta = 0;

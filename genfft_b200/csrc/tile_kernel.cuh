@@ -43,6 +43,8 @@ struct PassParams {
   int mode;                  // host side only: which compiled addressing mode to launch (enum Mode)
   float grid_frac;           // host side only: fraction of the resident-CTA capacity to launch (0 = all)
   uint32_t tiles_per_cta;    // 0: grid-stride loop over tiles (persistent grid); K > 0: CTA b owns tiles [b*K, b*K+K)
+  int tma_cols;              // experimental, off by default (slower, see plan.cu): column modes stage the L x C input
+                             // tile with one cp.async.bulk per row into the exchange buffer, mbarrier-signalled
   int inverse;               // conjugate on load and on store
   int in_real;               // 1: input is real scalars (imag = 0), FFT<T>::transform_real, fft.h:90-94
                              // 2: real part from `in`, imaginary part from `in2`, transform_interleave, fft.h:100-105
@@ -169,7 +171,11 @@ struct TileKernel {
   static constexpr size_t XBUF_BYTES = (NST > 1 || DIT || PAIR) ? sizeof(cpx<T>) * (size_t)PITCH * C : 0;
   // TMA mode: [exchange buffer][input buffer C*L][mbarrier]
   static constexpr size_t INBUF_OFFSET = (XBUF_BYTES + 127) & ~(size_t)127;
-  static constexpr size_t SMEM_BYTES = TMA ? INBUF_OFFSET + sizeof(cpx<T>) * (size_t)L * C + 16 : XBUF_BYTES;
+  static constexpr bool COLMODE = MODE == M_COL || MODE == M_COLTW || MODE == M_FIRST;
+  // column modes can stage their input tile by TMA into the exchange buffer itself (+ one mbarrier)
+  static constexpr size_t COLBAR_OFFSET = (XBUF_BYTES + 15) & ~(size_t)15;
+  static constexpr size_t SMEM_BYTES = TMA ? INBUF_OFFSET + sizeof(cpx<T>) * (size_t)L * C + 16
+                                           : (COLMODE && NST > 1 ? COLBAR_OFFSET + 16 : XBUF_BYTES);
   static constexpr bool GEN = MODE == M_GEN;
   static constexpr bool UNIT_IN = ROWLIKE;
   static constexpr bool UNIT_OUT = ROWLIKE || MODE == M_FIRST;
@@ -626,9 +632,46 @@ struct TileKernel {
       const uint32_t K = prm.tiles_per_cta;
       const uint32_t step = K ? 1u : gridDim.x;
       const uint32_t tile_end = K ? min(prm.ntiles, (blockIdx.x + 1u) * K) : prm.ntiles;
+      uint64_t* colbar = nullptr;
+      uint32_t colparity = 0;
+      if constexpr (COLMODE && NST > 1) {
+        if (prm.tma_cols) {
+          colbar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem) + COLBAR_OFFSET);
+          if (tid == 0) {
+            mbar_init(colbar, 1);
+            fence_barrier_init();
+          }
+          __syncthreads();
+        }
+      }
       for (uint32_t tile = K ? blockIdx.x * K : blockIdx.x; tile < tile_end; tile += step) {
         Tile t = decode(prm, tile);
-        load(prm, t, c_ld, u_ld, x);
+        bool staged = false;
+        if constexpr (COLMODE && NST > 1) {
+          if (prm.tma_cols) {
+            // TMA-staged tile: row idx of the tile (C adjacent columns = one contiguous segment) -> smem[idx][0..C)
+            cpx<T>* inbuf = smem;
+            if (tid < 32) {
+              if (tid == 0) mbar_arrive_expect_tx(colbar, (uint32_t)(L * C * sizeof(cpx<T>)));
+              __syncwarp();
+              const V* gsrc = reinterpret_cast<const V*>(prm.in) + t.in_off + (long long)t.col0 * prm.in_stride_c;
+              for (int r = tid; r < L; r += 32)
+                bulk_load(inbuf + (size_t)r * C, gsrc + (long long)r * prm.in_stride_i, (uint32_t)(C * sizeof(cpx<T>)), colbar);
+            }
+            mbar_wait(colbar, colparity);
+            colparity ^= 1;
+            const V* src = reinterpret_cast<const V*>(inbuf) + (size_t)u_ld * C + c_ld;
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+              V v = src[(size_t)i * TN * C];
+              x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
+            }
+            __syncthreads();  // everyone holds its points: the buffer becomes the exchange buffer
+            if constexpr (MODE == M_COLTW) apply_pass_twiddle(prm, t, t.col0 + c_ld, u_ld, x);
+            staged = true;
+          }
+        }
+        if (!staged) load(prm, t, c_ld, u_ld, x);
         int c = c_ld, u = u_ld;
         run_stages<0>(prm, x, smem, c, u, c_st, u_st);
         if constexpr (DIT) {
@@ -639,7 +682,8 @@ struct TileKernel {
           __syncthreads();
         } else {
           store(prm, t, c, u, x);
-          if (NST > 1) __syncthreads();  // next tile's first scatter must not overtake this tile's gathers
+          if (colbar) fence_proxy_async();  // generic-proxy accesses of the buffer before the next tile's TMA writes
+          if (NST > 1) __syncthreads();     // next tile's first scatter must not overtake this tile's gathers
         }
       }
     }

@@ -214,3 +214,30 @@ def test_c2_full_size_properties(comparand):
     want = y + 2 * torch.roll(y, 1, 0)
     rel = ((y2 - want).abs().double() ** 2).sum().sqrt().item() / (want.abs().double() ** 2).sum().sqrt().item()
     assert rel <= oracle.tolerance(n, np.float32)
+
+
+@pytest.mark.parametrize("lg,dt", [(25, np.float32), (27, np.float32), (25, np.float64)])
+def test_sizes_beyond_the_reference_maximum(lg, dt):
+    """N = 2^25 ... 2^27 (the reference stops at 2^23): a spectral line lands in the right bin with the right
+    amplitude, Parseval holds, and the unscaled inverse returns n * x."""
+    n = 1 << lg
+    cd = torch.complex64 if dt == np.float32 else torch.complex128
+    plan = g.FFT(n, dt)
+    k0 = 123457 % n
+    t = torch.arange(n, device="cuda", dtype=torch.float64)
+    gen = torch.Generator(device="cuda").manual_seed(lg)
+    noise = torch.view_as_complex(torch.rand((n, 2), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1)
+    phase = 2 * np.pi * ((k0 * t) % n) / n
+    x = (torch.polar(torch.ones_like(phase), phase) + 1e-3 * noise).to(cd)
+    del t, phase, noise
+    y = torch.empty_like(x)
+    plan.forward(y, x)
+    peak = y[k0].item()
+    assert abs(peak - n) / n < 1e-4
+    ex = (x.abs().double() ** 2).sum().item()
+    ey = (y.abs().double() ** 2).sum().item()
+    assert abs(ey / (n * ex) - 1) < (1e-5 if dt == np.float32 else 1e-12)
+    z = torch.empty_like(x)
+    plan.inverse(z, y)
+    err = (z / n - x).abs().max().item()
+    assert err < (1e-4 if dt == np.float32 else 1e-12), plan.describe()

@@ -8,11 +8,14 @@ mkdir -p "$OUT" "$OBJ"
 NVCC=${NVCC:-nvcc}
 FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $GENFFT_NVCC_EXTRA"
 pids=()
+for k in 0 1 2 3; do
+  $NVCC $FLAGS -DGENFFT_CSET=$k -c "$HERE/chains_inst.cu" -o "$OBJ/chains_$k.o" & pids+=($!)
+done
 for k in 0 1 2 3 4 5; do
   $NVCC $FLAGS -DGENFFT_KSET=$k -c "$HERE/kernels_inst.cu" -o "$OBJ/kernels_$k.o" & pids+=($!)
 done
 $NVCC $FLAGS -c "$HERE/plan.cu" -o "$OBJ/plan.o" & pids+=($!)
 $NVCC $FLAGS -c "$HERE/host_exec.cu" -o "$OBJ/host_exec.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libgenfft_cuda.so" "$OBJ"/kernels_*.o "$OBJ/plan.o" "$OBJ/host_exec.o"
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libgenfft_cuda.so" "$OBJ"/kernels_*.o "$OBJ"/chains_*.o "$OBJ/plan.o" "$OBJ/host_exec.o"
 echo "built $OUT/libgenfft_cuda.so"

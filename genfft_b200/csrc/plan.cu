@@ -98,6 +98,24 @@ static std::vector<KernelEntry>& registry(int precision) {
   return precision == GENFFT_CUDA_F32 ? f32 : f64;
 }
 
+static const ChainEntry* find_chain(int precision, const KernelEntry* ka, int ma, const KernelEntry* kb, int mb, int inv) {
+  static std::vector<ChainEntry> chains;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    register_chains_0(chains);
+    register_chains_1(chains);
+    register_chains_2(chains);
+    register_chains_3(chains);
+  });
+  if (ka->P != 16 || kb->P != 16) return nullptr;
+  const int prec = precision == GENFFT_CUDA_F32 ? 0 : 1;
+  for (auto& e : chains)
+    if (e.precision == prec && e.la == ka->L && e.ca == ka->C && e.ma == ma && e.lb == kb->L && e.cb == kb->C &&
+        e.mb == mb && e.inv == inv)
+      return &e;
+  return nullptr;
+}
+
 // Kernel shape for a length-L pass.  Narrow (contiguous batched) use takes the fewest sequences per CTA.  Wide (column)
 // use wants row segments of at least 128 bytes and CTAs of ~256 threads in float / ~128 in double (128 registers per
 // thread there): measured best with one-shot grids (tools/sweep.sh).  Tuning knobs: GENFFT_CUDA_WIDE_C_{F32,F64}
@@ -548,6 +566,46 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
   return GENFFT_CUDA_OK;
 }
 
+// One launch for two consecutive passes with the intermediate kept in L2 (chain_kernel.cuh).
+static int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaStream_t stream) {
+  const size_t need = 1 + (size_t)cp.ngroups;
+  {
+    std::lock_guard<std::mutex> lk(plan->mu);
+    if (plan->chain_ctr_count < need) {
+      if (plan->chain_ctr) {
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaFree(plan->chain_ctr));
+        plan->chain_ctr = nullptr;
+        plan->chain_ctr_count = 0;
+      }
+      const size_t cap = std::max<size_t>(need, 4096);
+      if (cudaMalloc(&plan->chain_ctr, cap * sizeof(uint32_t)) != cudaSuccess)
+        return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc of %zu chain counters failed", cap);
+      plan->chain_ctr_count = cap;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    auto key = std::make_pair(plan->device, ce->func);
+    if (!g_occupancy.count(key)) {
+      if (ce->smem > 48 * 1024)
+        CU_TRY(cudaFuncSetAttribute(ce->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce->smem));
+      int occ = 0;
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ce->func, ce->threads, ce->smem));
+      if (occ < 1) return fail(GENFFT_CUDA_ERR_CUDA, "chain kernel cannot be resident (smem %zu)", ce->smem);
+      g_occupancy[key] = occ;
+    }
+  }
+  cp.ctr = static_cast<uint32_t*>(plan->chain_ctr);
+  CU_TRY(cudaMemsetAsync(plan->chain_ctr, 0, need * sizeof(uint32_t), stream));
+  const unsigned long long grid = (unsigned long long)cp.ngroups * (cp.ta + cp.tb);
+  if (grid == 0 || grid > 0x7fffffffULL) return fail(GENFFT_CUDA_ERR_SIZE, "chain grid of %llu tiles", grid);
+  ce->launch(cp, (unsigned)grid, stream);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
 template <typename T>
 static int launch_copy_t(const CopyParams& cp, long long batch, cudaStream_t stream) {
   if (cp.rows <= 0 || cp.cols <= 0 || batch <= 0) return GENFFT_CUDA_OK;
@@ -730,11 +788,135 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
   }
   if (cur.ptr != out.ptr) return fail(GENFFT_CUDA_ERR_ARG, "internal: pass chain did not end in the output buffer");
 
-  // ---- execute.  Consecutive passes along the same dimension form a segment.  Experimental knob
-  // GENFFT_CUDA_L2_GROUP_MB > 0 runs a segment's independent units (sequences of a batch, rows, columns) in groups of
-  // that size, all passes of a group back to back, hoping to read the intermediate back from the 126 MB L2 instead
-  // of HBM.  Measured on B200 it LOSES (C5 10.7 -> 13.4 ms at 64 MiB groups, 19.7 ms at 16 MiB; C4 4.9 -> 6.3 ms):
-  // the per-group kernels are single-wave and launch/latency-bound, so it is off by default. ----
+  // parameters of step s for the units [g0, g0 + gn) of its segment (sequences of a batch / rows, or columns)
+  auto make_params = [&](size_t s, long long g0, long long gn, PassParams* pp) -> int {
+    const Step& st = steps[s];
+    const bool col = st.col;
+    const size_t src_es = st.real_in ? es / 2 : es;
+    // element offset of the group inside a buffer: sequences are `pitch` apart, columns are adjacent
+    auto off = [&](const View& v) { return col ? g0 : g0 * v.pitch; };
+    const char* src = (const char*)io[s].src.ptr + (size_t)off(io[s].src) * src_es;
+    char* dst = (char*)io[s].dst.ptr + (size_t)off(io[s].dst) * es;
+    const bool peers_out = fs && fs->peers && s == n - 1;
+    PassParams p = st.col ? emit_col(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev)
+                          : emit_1d(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev);
+    if (st.real_in) {
+      p.in_real = in2 ? 2 : 1;
+      p.in2 = in2 ? (const char*)in2 + (size_t)off(io[s].src) * src_es : nullptr;
+      p.mode = M_GEN;
+    }
+    p.grid_frac = (s == n - 1) ? plan->grid_frac[1] : plan->grid_frac[0];
+    if (df && s == n - 1) {
+      // pair tiles: Ns/C tiles of {p} U {Ns-p} plus one tile for column 0
+      p.mode = M_COLTWDIT;
+      p.n2 = (uint32_t)(st.ps->Ns / st.ps->k->C) + 1u;
+      p.ntiles = (uint32_t)(gn * p.n2);
+      p.dit_half = df->half;
+      p.dit_a = df->dit_a;
+      p.dit_tw = df->dit_tw;
+    }
+    if (fs && s == n - 1) {
+      p.mode = M_GEN;
+      const long long Ns = (st.N == st.ps->R) ? 1 : st.ps->Ns;
+      const int sh = fs->part_log2 - ilog2(Ns);
+      if (sh < 0) return fail(GENFFT_CUDA_ERR_SIZE, "part size 2^%d smaller than pass stride %lld", fs->part_log2, Ns);
+      p.out_split_log2 = sh;
+      if (fs->peers) {
+        p.use_peers = 1;
+        for (int g = 0; g < fs->npeers && g < kMaxPeers; g++)
+          p.out_peer[g] = (char*)fs->peers[g] + (size_t)(fs->peer_offset + off(io[s].dst)) * es;
+      } else {
+        p.out_stride_khi = fs->part_stride;
+      }
+    }
+    *pp = p;
+    return GENFFT_CUDA_OK;
+  };
+
+  // L2-resident chain of the last two passes of a segment (chain_kernel.cuh).  The B tiles of a group may depend only
+  // on the A tiles of the same group:
+  //   * whole units (rows / transforms / column blocks) when the segment has two passes, or B is the pair-tile split
+  //     pass of a real transform, or B stores to peers;
+  //   * the column classes {p2 in [g*W, (g+1)*W)} of a three-pass transform N = R1*R2*R3: pass 2 (Ns = R1) writes
+  //     z[a*R1*R2 + p2 + k*R1], pass 3 (Ns = R1*R2) reads z[p3 + i*R1*R2] with p3 = p2 + k*R1, so all of pass 3's
+  //     columns with p3 mod R1 in the class depend exactly on pass 2's tiles of that class.
+  // Returns 1 if the pair was launched, 0 if the caller has to run the passes one by one, < 0 on error.
+  const long long chain_target = (long long)env_int("GENFFT_CUDA_CHAIN_KB", 4096) << 10;
+  const long long chain_max = (long long)env_int("GENFFT_CUDA_CHAIN_MAX_KB", 32768) << 10;
+  const bool chain_on = env_int("GENFFT_CUDA_CHAIN", 1) != 0 && plan->grid_frac[0] >= 1.f && plan->grid_frac[1] >= 1.f &&
+                        !env_int("GENFFT_CUDA_PERSISTENT", 0);
+  auto try_chain = [&](size_t sa, size_t sb, bool three, long long units, int* rc_out) -> bool {
+    *rc_out = GENFFT_CUDA_OK;
+    const Step &A = steps[sa], &B = steps[sb];
+    if (A.brev || A.real_in || B.brev || B.real_in) return false;
+    if (io[sb].dst.ptr == io[sa].src.ptr) return false;
+    const KernelEntry *ka = A.ps->k, *kb = B.ps->k;
+    if (ka->threads != kb->threads) return false;
+    const bool col = A.col;
+    const int cmax = std::max(ka->C, kb->C);
+    ChainParams cp;
+    memset(&cp, 0, sizeof cp);
+    const bool intra = three && !col && !(df && sb == n - 1) && !(fs && sb == n - 1);
+    if (intra) {
+      const long long R1 = A.ps->Ns, R2 = A.ps->R, R3 = B.ps->R, N = A.N;
+      if (B.ps->Ns != R1 * R2 || R1 * R2 * R3 != N || cmax > R1) return false;
+      long long W = cmax;
+      while (W * 2 <= R1 && N / R1 * (W * 2) * (long long)es <= chain_target) W *= 2;
+      if (N / R1 * W * (long long)es > chain_max) return false;
+      int rc = make_params(sa, 0, 1, &cp.a);
+      if (!rc) rc = make_params(sb, 0, 1, &cp.b);
+      if (rc) { *rc_out = rc; return false; }
+      if (cp.a.mode != M_COLTW || cp.b.mode != M_COLTW) return false;
+      cp.a.ncols = (int)W;
+      cp.a.n2 = (uint32_t)(W / ka->C);
+      cp.a.ntiles = cp.a.n1 * cp.a.n2;  // n1 = R3 blocks a
+      cp.b.n1 = (uint32_t)R2;            // t1 = k: columns p3 = p2 + k*R1
+      cp.b.in_t1 = R1;
+      cp.b.out_t1 = R1;
+      cp.b.p_t1 = (int)R1;
+      cp.b.ncols = (int)W;
+      cp.b.n2 = (uint32_t)(W / kb->C);
+      cp.b.ntiles = cp.b.n1 * cp.b.n2;
+      cp.gdiv = (uint32_t)(R1 / W);
+      cp.a_in_hi = io[sa].src.pitch; cp.a_out_hi = io[sa].dst.pitch;
+      cp.b_in_hi = io[sb].src.pitch; cp.b_out_hi = io[sb].dst.pitch;
+      cp.a_in_lo = cp.a_out_lo = cp.b_in_lo = cp.b_out_lo = W;
+      cp.a_p_lo = cp.b_p_lo = (uint32_t)W;
+      cp.ngroups = (uint32_t)(units * cp.gdiv);
+    } else {
+      const long long unit_bytes = A.N * (long long)es;
+      long long U = 1;
+      while (U * 2 * unit_bytes <= chain_target) U *= 2;
+      const long long umin = col ? cmax : 1;
+      U = std::max(U, umin);
+      while (U > umin && units % U) U /= 2;
+      if (units % U || U * unit_bytes > chain_max) return false;
+      int rc = make_params(sa, 0, U, &cp.a);
+      if (!rc) rc = make_params(sb, 0, U, &cp.b);
+      if (rc) { *rc_out = rc; return false; }
+      cp.gdiv = 0x7fffffffu;
+      if (col) {
+        cp.a_in_lo = cp.a_out_lo = cp.b_in_lo = cp.b_out_lo = U;
+      } else {
+        cp.a_in_lo = U * io[sa].src.pitch; cp.a_out_lo = U * io[sa].dst.pitch;
+        cp.b_in_lo = U * io[sb].src.pitch; cp.b_out_lo = U * io[sb].dst.pitch;
+      }
+      cp.ngroups = (uint32_t)(units / U);
+    }
+    const ChainEntry* ce = find_chain(plan->precision, ka, cp.a.mode, kb, cp.b.mode, inverse ? 1 : 0);
+    if (!ce) return false;
+    cp.ta = cp.a.ntiles;
+    cp.tb = cp.b.ntiles;
+    if (!cp.ta || !cp.tb || !cp.ngroups) return false;
+    cp.lag = (uint32_t)std::min<long long>(std::max(1, env_int("GENFFT_CUDA_CHAIN_LAG", 2)), cp.ngroups);
+    *rc_out = launch_chain(plan, ce, cp, stream);
+    return *rc_out == GENFFT_CUDA_OK;
+  };
+
+  // ---- execute.  Consecutive passes along the same dimension form a segment.  The last two passes of a segment run
+  // as one L2-resident chain when a chain kernel exists for their shapes.  (The older experiment GENFFT_CUDA_L2_GROUP_MB
+  // ran a segment group by group with one launch per pass and group; it LOST -- C5 10.7 -> 13.4 ms at 64 MiB groups --
+  // because those launches are single-wave and latency-bound.  It is kept for reference, off by default.) ----
   const long long l2_group_bytes = (long long)env_int("GENFFT_CUDA_L2_GROUP_MB", 0) << 20;
   size_t seg_begin = 0;
   while (seg_begin < n) {
@@ -743,6 +925,33 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     const bool col = steps[seg_begin].col;
     const long long units = col ? cols : count;
     const long long unit_bytes = steps[seg_begin].N * (long long)es;
+    size_t run_end = seg_end;  // passes [seg_begin, run_end) are launched one by one
+    bool chained = false;
+    int crc = GENFFT_CUDA_OK;
+    if (seg_end - seg_begin >= 2 && chain_on && l2_group_bytes == 0) {
+      // passes before the pair first, over all units
+      for (size_t s = seg_begin; s + 2 < seg_end; s++) {
+        PassParams p;
+        int rc = make_params(s, 0, units, &p);
+        if (!rc) rc = launch_pass(plan, *steps[s].ps, p, stream);
+        if (rc) return rc;
+      }
+      chained = try_chain(seg_end - 2, seg_end - 1, seg_end - seg_begin == 3, units, &crc);
+      if (crc) return crc;
+      if (chained) {
+        seg_begin = seg_end;
+        continue;
+      }
+      // no chain for this pair: run the two remaining passes plainly
+      for (size_t s = seg_end - 2; s < seg_end; s++) {
+        PassParams p;
+        int rc = make_params(s, 0, units, &p);
+        if (!rc) rc = launch_pass(plan, *steps[s].ps, p, stream);
+        if (rc) return rc;
+      }
+      seg_begin = seg_end;
+      continue;
+    }
     long long group = units;
     if (seg_end - seg_begin >= 2 && l2_group_bytes > 0 && !copy_in) {
       group = std::max<long long>(1, l2_group_bytes / unit_bytes);
@@ -755,46 +964,10 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     }
     for (long long g0 = 0; g0 < units; g0 += group) {
       const long long gn = std::min(group, units - g0);
-      for (size_t s = seg_begin; s < seg_end; s++) {
-        const Step& st = steps[s];
-        const size_t src_es = st.real_in ? es / 2 : es;
-        // element offset of the group inside a buffer: sequences are `pitch` apart, columns are adjacent
-        auto off = [&](const View& v) { return col ? g0 : g0 * v.pitch; };
-        const char* src = (const char*)io[s].src.ptr + (size_t)off(io[s].src) * src_es;
-        char* dst = (char*)io[s].dst.ptr + (size_t)off(io[s].dst) * es;
-        const bool peers_out = fs && fs->peers && s == n - 1;
-        PassParams p = st.col ? emit_col(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev)
-                              : emit_1d(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev);
-        if (st.real_in) {
-          p.in_real = in2 ? 2 : 1;
-          p.in2 = in2 ? (const char*)in2 + (size_t)off(io[s].src) * src_es : nullptr;
-          p.mode = M_GEN;
-        }
-        p.grid_frac = (s == n - 1) ? plan->grid_frac[1] : plan->grid_frac[0];
-        if (df && s == n - 1) {
-          // pair tiles: Ns/C tiles of {p} U {Ns-p} plus one tile for column 0
-          p.mode = M_COLTWDIT;
-          p.n2 = (uint32_t)(st.ps->Ns / st.ps->k->C) + 1u;
-          p.ntiles = (uint32_t)(gn * p.n2);
-          p.dit_half = df->half;
-          p.dit_a = df->dit_a;
-          p.dit_tw = df->dit_tw;
-        }
-        if (fs && s == n - 1) {
-          p.mode = M_GEN;
-          const long long Ns = (st.N == st.ps->R) ? 1 : st.ps->Ns;
-          const int sh = fs->part_log2 - ilog2(Ns);
-          if (sh < 0) return fail(GENFFT_CUDA_ERR_SIZE, "part size 2^%d smaller than pass stride %lld", fs->part_log2, Ns);
-          p.out_split_log2 = sh;
-          if (fs->peers) {
-            p.use_peers = 1;
-            for (int g = 0; g < fs->npeers && g < kMaxPeers; g++)
-              p.out_peer[g] = (char*)fs->peers[g] + (size_t)(fs->peer_offset + off(io[s].dst)) * es;
-          } else {
-            p.out_stride_khi = fs->part_stride;
-          }
-        }
-        int rc = launch_pass(plan, *st.ps, p, stream);
+      for (size_t s = seg_begin; s < run_end; s++) {
+        PassParams p;
+        int rc = make_params(s, g0, gn, &p);
+        if (!rc) rc = launch_pass(plan, *steps[s].ps, p, stream);
         if (rc) return rc;
       }
     }
@@ -976,6 +1149,7 @@ int genfft_cuda_plan_destroy(genfft_cuda_plan_t plan) {
   if (!plan) return GENFFT_CUDA_OK;
   Plan* p = plan;
   if (p->scratch) cudaFree(p->scratch);
+  if (p->chain_ctr) cudaFree(p->chain_ctr);
   if (p->aux) cudaFree(p->aux);
   if (p->stage_in) cudaFree(p->stage_in);
   if (p->stage_out) cudaFree(p->stage_out);

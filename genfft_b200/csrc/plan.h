@@ -53,6 +53,8 @@ struct Plan {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   size_t scratch_need = 0;  // upper bound known at plan time (0 if none / depends on exec args)
+  void* chain_ctr = nullptr;  // ticket + per-group counters of the L2-resident pass chains (chain_kernel.cuh)
+  size_t chain_ctr_count = 0;
   void* aux = nullptr;  // device staging owned by device-pointer entry points (c2r pre-processed spectrum)
   size_t aux_bytes = 0;
   // host-pointer staging

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <vector>
 #include "tile_kernel.cuh"
+#include "chain_kernel.cuh"
 
 namespace genfft_cuda {
 
@@ -69,6 +70,62 @@ KernelEntry make_entry() {
   }
   return e;
 }
+
+// ---- L2-resident pass chains (chain_kernel.cuh): pairs of wide shapes with equal CTA sizes ----
+struct ChainEntry {
+  int precision;  // 0: float, 1: double (GENFFT_CUDA_F32 / F64)
+  int la, ca, ma, lb, cb, mb, inv;
+  int threads;
+  size_t smem;
+  const void* func;
+  void (*launch)(const ChainParams& cp, unsigned grid, cudaStream_t stream);
+};
+
+template <typename T, class KA, class KB>
+void launch_chain_t(const ChainParams& cp, unsigned grid, cudaStream_t stream) {
+  constexpr size_t smem = KA::SMEM_BYTES > KB::SMEM_BYTES ? KA::SMEM_BYTES : KB::SMEM_BYTES;
+  fft_chain_kernel<T, KA, KB><<<grid, KA::THREADS, smem, stream>>>(cp);
+}
+
+// INV applies to the compile-time-direction modes; M_GEN takes the direction from PassParams::inverse
+template <typename T, int LA, int CA, int MA, int LB, int CB, int MB, bool INV>
+void add_chain(std::vector<ChainEntry>& v) {
+  using KA = TileKernel<T, LA, 16, CA, MA, MA == M_GEN ? false : INV>;
+  using KB = TileKernel<T, LB, 16, CB, MB, MB == M_GEN ? false : INV>;
+  ChainEntry e = {};
+  e.precision = sizeof(T) == 4 ? 0 : 1;
+  e.la = LA; e.ca = CA; e.ma = MA;
+  e.lb = LB; e.cb = CB; e.mb = MB;
+  e.inv = INV ? 1 : 0;
+  e.threads = KA::THREADS;
+  e.smem = KA::SMEM_BYTES > KB::SMEM_BYTES ? KA::SMEM_BYTES : KB::SMEM_BYTES;
+  e.func = reinterpret_cast<const void*>(&fft_chain_kernel<T, KA, KB>);
+  e.launch = &launch_chain_t<T, KA, KB>;
+  v.push_back(e);
+}
+
+// every mode pair the plans chain, for one pair of shapes
+template <typename T, int LA, int CA, int LB, int CB>
+void add_chain_shapes(std::vector<ChainEntry>& v) {
+  add_chain<T, LA, CA, M_FIRST, LB, CB, M_COLTW, false>(v);  // 2-pass 1D, rows of 2D
+  add_chain<T, LA, CA, M_FIRST, LB, CB, M_COLTW, true>(v);
+  add_chain<T, LA, CA, M_COL, LB, CB, M_COLTW, false>(v);    // 2-pass columns
+  add_chain<T, LA, CA, M_COL, LB, CB, M_COLTW, true>(v);
+  add_chain<T, LA, CA, M_COLTW, LB, CB, M_COLTW, false>(v);  // passes 2+3 of a 3-pass transform
+  add_chain<T, LA, CA, M_COLTW, LB, CB, M_COLTW, true>(v);
+  add_chain<T, LA, CA, M_COLTW, LB, CB, M_COLTWDIT, false>(v);  // ... of a real transform (split fused)
+  add_chain<T, LA, CA, M_FIRST, LB, CB, M_COLTWDIT, false>(v);
+  add_chain<T, LA, CA, M_FIRST, LB, CB, M_GEN, false>(v);    // distributed 2D: B stores to the peers
+  add_chain<T, LA, CA, M_FIRST, LB, CB, M_GEN, true>(v);
+  add_chain<T, LA, CA, M_COL, LB, CB, M_GEN, false>(v);
+  add_chain<T, LA, CA, M_COL, LB, CB, M_GEN, true>(v);
+}
+
+// defined in chains_inst.cu (compiled once per GENFFT_CSET)
+void register_chains_0(std::vector<ChainEntry>& v);
+void register_chains_1(std::vector<ChainEntry>& v);
+void register_chains_2(std::vector<ChainEntry>& v);
+void register_chains_3(std::vector<ChainEntry>& v);
 
 // defined in kernels_inst.cu (compiled once per GENFFT_KSET)
 void register_kernels_f32_small(std::vector<KernelEntry>& v);

@@ -154,6 +154,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Cache operators of the data loads/stores.  The stand-alone kernels use the defaults; the L2-resident pass chains
+// (chain_kernel.cuh) stream their HBM-side traffic (evict-first) and read the intermediate, which another SM wrote
+// during the same launch, past the non-coherent L1.
+enum CacheOp { CO_DEFAULT = 0, CO_STREAM = 1, CO_L2ONLY = 2 };
+template <int OP, typename V>
+__device__ __forceinline__ V ld_data(const V* p) {
+  if constexpr (OP == CO_STREAM) return __ldcs(p);
+  else if constexpr (OP == CO_L2ONLY) return __ldcg(p);
+  else return *p;
+}
+template <int OP, typename V>
+__device__ __forceinline__ void st_data(V* p, const V& v) {
+  if constexpr (OP == CO_STREAM) __stcs(p, v);
+  else *p = v;
+}
+
 template <typename T, int L, int P, int C, int MODE, bool INV>
 struct TileKernel {
   static constexpr int TN = L / P;
@@ -256,6 +272,7 @@ struct TileKernel {
     for (int i = 1; i < P; i++) x[i] = cmul(x[i], cmul(a, cpx<T>(b[i].x, b[i].y)));
   }
 
+  template <int LDOP = CO_DEFAULT>
   static __device__ __forceinline__ void load(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {
     bool valid;
     const uint32_t col = column_of(prm, t, c, valid);
@@ -266,7 +283,7 @@ struct TileKernel {
           const V* src = reinterpret_cast<const V*>(prm.in) + base + u;
 #pragma unroll
           for (int i = 0; i < P; i++) {
-            V v = src[i * TN];
+            V v = ld_data<LDOP>(src + i * TN);
             x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
           }
         } else {
@@ -274,7 +291,7 @@ struct TileKernel {
           const long long step = (long long)TN * prm.in_stride_i;
 #pragma unroll
           for (int i = 0; i < P; i++) {
-            V v = *src;
+            V v = ld_data<LDOP>(src);
             src += step;
             x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
           }
@@ -301,7 +318,7 @@ struct TileKernel {
         } else if (prm.in_real) {
           x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], T(0));
         } else {
-          V v = reinterpret_cast<const V*>(prm.in)[off];
+          V v = ld_data<LDOP>(reinterpret_cast<const V*>(prm.in) + off);
           x[i] = cpx<T>(v.x, v.y);
         }
       } else {
@@ -316,6 +333,7 @@ struct TileKernel {
     }
   }
 
+  template <int STOP = CO_DEFAULT>
   static __device__ __forceinline__ void store(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {
     const uint32_t col = t.col0 + c;
     if (col >= (uint32_t)prm.ncols) return;
@@ -328,7 +346,7 @@ struct TileKernel {
           V v;
           v.x = x[i].x;
           v.y = INV ? -x[i].y : x[i].y;
-          dst[i * TN] = v;
+          st_data<STOP>(dst + i * TN, v);
         }
       } else {
         V* dst = reinterpret_cast<V*>(prm.out) + base + (long long)u * prm.out_stride_k;
@@ -338,7 +356,7 @@ struct TileKernel {
           V v;
           v.x = x[i].x;
           v.y = INV ? -x[i].y : x[i].y;
-          *dst = v;
+          st_data<STOP>(dst, v);
           dst += step;
         }
       }
@@ -350,14 +368,14 @@ struct TileKernel {
       v.x = x[i].x;
       v.y = prm.inverse ? -x[i].y : x[i].y;
       if (prm.out_split_log2 < 0) {
-        reinterpret_cast<V*>(prm.out)[base + (long long)k * prm.out_stride_k] = v;
+        st_data<STOP>(reinterpret_cast<V*>(prm.out) + base + (long long)k * prm.out_stride_k, v);
       } else {
         const int khi = k >> prm.out_split_log2;
         const int klo = k & ((1 << prm.out_split_log2) - 1);
         if (prm.use_peers) {
           reinterpret_cast<V*>(prm.out_peer[khi])[base + (long long)klo * prm.out_stride_k] = v;
         } else {
-          reinterpret_cast<V*>(prm.out)[base + (long long)klo * prm.out_stride_k + (long long)khi * prm.out_stride_khi] = v;
+          st_data<STOP>(reinterpret_cast<V*>(prm.out) + base + (long long)klo * prm.out_stride_k + (long long)khi * prm.out_stride_khi, v);
         }
       }
     }
@@ -562,6 +580,36 @@ struct TileKernel {
         g.y = -f.y;
         dst[2 * M - q] = g;
       }
+    }
+  }
+
+  // One tile of a pass chain (chain_kernel.cuh): the CTA transforms tile `tile` of the group whose element offsets
+  // (in_g, out_g) and twiddle-column offset p_g are added to the pass's group-0 addressing.
+  template <int LDOP, int STOP>
+  static __device__ __forceinline__ void tile_once(const PassParams& prm, cpx<T>* smem, uint32_t tile, long long in_g,
+                                                   long long out_g, uint32_t p_g) {
+    static_assert(!TMA, "chains run the plain tile modes");
+    const int tid = threadIdx.x;
+    const bool ld_b = GEN ? prm.map_load != 0 : ROWLIKE;
+    const bool st_b = GEN ? prm.map_store != 0 : (ROWLIKE || MODE == M_FIRST);
+    const int c_ld = ld_b ? tid / TN : tid % C;
+    const int u_ld = ld_b ? tid % TN : tid / C;
+    const int c_st = st_b ? tid / TN : tid % C;
+    const int u_st = st_b ? tid % TN : tid / C;
+    cpx<T> x[P];
+    Tile t = decode(prm, tile);
+    t.in_off += in_g;
+    t.out_off += out_g;
+    t.p_base += p_g;
+    load<LDOP>(prm, t, c_ld, u_ld, x);
+    int c = c_ld, u = u_ld;
+    run_stages<0>(prm, x, smem, c, u, c_st, u_st);
+    if constexpr (DIT) {
+      dit_store(prm, t, c, u, x, smem);
+    } else if constexpr (PAIR) {
+      pair_dit_store(prm, t, c, u, x, smem);
+    } else {
+      store<STOP>(prm, t, c, u, x);
     }
   }
 

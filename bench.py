@@ -124,23 +124,29 @@ def reference_arm(args, rank: int, world: int) -> int:
         return 0
     ref = oracle.Ref()
     threads = ref.hardware_threads()
-    # bounded sample per step: calibrate ~1.5 s of wall per step
+    # One step = one sweep of the reference over a bounded sample of the batch ARRAY: `per_step` distinct transforms,
+    # host array in -> host array out, split over all host threads (the reference has no batch API; this is the loop
+    # a CPU caller writes, and the same host-buffer contract our e2e figure is timed on).
+    per_step = min(BATCH * world, 16384)
+    t = ref.bench_c2c_array(N_FFT, per_step, threads, args.warmup, args.steps)
+    ms = 1e3 * t
+    value = 5.0 * N_FFT * math.log2(N_FFT) * per_step / t / 1e9
+    # the reference's own benchmark loop (fft_bench.cpp FFT_1D: one in/out buffer, fresh input per iteration) keeps
+    # the 64 KiB working set in cache; reported beside the streaming figure
     t_cal = ref.bench_c2c(N_FFT, 64 * threads, threads)
-    per_step = max(threads, int(64 * threads * 1.5 / max(t_cal, 1e-6)))
-    per_step = min(per_step, BATCH * world)
-    for _ in range(args.warmup):
-        ref.bench_c2c(N_FFT, per_step, threads)
-    t = 0.0
-    for _ in range(args.steps):
-        t += ref.bench_c2c(N_FFT, per_step, threads)
-    ms = 1e3 * t / args.steps
-    value = 5.0 * N_FFT * math.log2(N_FFT) * per_step / (t / args.steps) / 1e9
-    sample = f"{per_step} of {BATCH * world} transforms per step, {threads} host threads, fft_bench.cpp FFT_1D loop (forward only)"
+    n_res = max(threads, int(64 * threads * 3.0 / max(t_cal, 1e-6)))
+    t_res = ref.bench_c2c(N_FFT, n_res, threads)
+    resident = 5.0 * N_FFT * math.log2(N_FFT) * n_res / t_res / 1e9
+    sample = (f"{per_step} of {BATCH * world} transforms per step as a host batch array (in and out each "
+              f"{per_step * N_FFT * 8 >> 20} MiB, streamed from/to DRAM), {threads} host threads, forward only")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic U(-1,1), std::mt19937_64 per thread", "config": config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+                         "cache_resident_value": resident,
+                         "cache_resident_sample": f"{n_res} transforms through one in/out buffer per thread "
+                                                  f"(restated fft_bench.cpp FFT_1D loop)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_build": ref.describe(),
     }
@@ -273,15 +279,24 @@ def main() -> int:
             import oracle
             ref = oracle.Ref()
             threads = ref.hardware_threads()
+            # bounded sample of the same workload: sweeps over a 16384-transform host batch array (in -> out, DRAM-
+            # streaming like the e2e path), ~10 s of CPU work; beside it the reference's own cache-resident bench loop
+            count = 16384
+            t_one_sweep = ref.bench_c2c_array(N_FFT, count, threads, 1, 2)
+            reps = max(2, min(2000, int(10.0 / max(t_one_sweep, 1e-4))))
+            t_cpu = ref.bench_c2c_array(N_FFT, count, threads, 1, reps)
             t_cal = ref.bench_c2c(N_FFT, 32 * threads, threads)
-            count = max(threads, int(32 * threads * 10.0 / max(t_cal, 1e-6)))
-            t_cpu = ref.bench_c2c(N_FFT, count, threads)
+            n_res = max(threads, int(32 * threads * 3.0 / max(t_cal, 1e-6)))
+            t_res = ref.bench_c2c(N_FFT, n_res, threads)
             t_one = ref.bench_c2c(N_FFT, 2048, 1)
             line["cpu_baseline"] = {
                 "value": 5.0 * N_FFT * 12 * count / t_cpu / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
-                "sample": f"{count} transforms ({count / BATCH:.1f} x the {BATCH}-transform batch, ~10 s of CPU work), "
-                          f"fresh U(-1,1) input per transform, {threads} threads "
-                          f"(restated fft_bench.cpp FFT_1D loop, forward only); {ref.describe()}",
+                "sample": f"{reps} sweeps over a host batch array of {count} transforms ({count / BATCH:.2f} of the batch; "
+                          f"in and out each {count * N_FFT * 8 >> 20} MiB, streamed from/to DRAM; ~{reps * t_cpu:.0f} s of "
+                          f"CPU work), {threads} threads, forward only; {ref.describe()}",
+                "cache_resident_value": 5.0 * N_FFT * 12 * n_res / t_res / 1e9,
+                "cache_resident_sample": f"{n_res} transforms through one in/out buffer per thread, fresh U(-1,1) input "
+                                         f"per transform (restated fft_bench.cpp FFT_1D loop)",
                 "single_core_value": 5.0 * N_FFT * 12 * 2048 / t_one / 1e9,
             }
         except Exception as e:  # the oracle is a checker; its absence must not hide the GPU numbers

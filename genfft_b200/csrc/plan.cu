@@ -584,23 +584,35 @@ static int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaS
       plan->chain_ctr_count = cap;
     }
   }
+  int occ = 0;
   {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
     auto key = std::make_pair(plan->device, ce->func);
-    if (!g_occupancy.count(key)) {
+    auto it = g_occupancy.find(key);
+    if (it == g_occupancy.end()) {
       if (ce->smem > 48 * 1024)
         CU_TRY(cudaFuncSetAttribute(ce->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce->smem));
-      int occ = 0;
       CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ce->func, ce->threads, ce->smem));
       if (occ < 1) return fail(GENFFT_CUDA_ERR_CUDA, "chain kernel cannot be resident (smem %zu)", ce->smem);
       g_occupancy[key] = occ;
+    } else {
+      occ = it->second;
     }
   }
+  const unsigned long long total = (unsigned long long)cp.ngroups * (cp.ta + cp.tb);
+  if (total == 0 || total > 0x7fffffffULL) return fail(GENFFT_CUDA_ERR_SIZE, "chain of %llu tiles", total);
+  const unsigned long long resident = (unsigned long long)plan->num_sms * occ;
+  // B(g) is handed out `lag` groups after A(g): far enough that A(g)'s tiles, which the resident CTAs may still be
+  // working on, are done by then (no spinning), near enough that A(g)'s output is still in L2
+  if (cp.lag == 0) {
+    const unsigned long long per = cp.ta + cp.tb;
+    cp.lag = (uint32_t)std::min<unsigned long long>(8, 1 + (3 * resident / 2 + per - 1) / per);
+    cp.lag = std::max(cp.lag, 2u);
+  }
+  cp.lag = std::min(cp.lag, cp.ngroups);
   cp.ctr = static_cast<uint32_t*>(plan->chain_ctr);
   CU_TRY(cudaMemsetAsync(plan->chain_ctr, 0, need * sizeof(uint32_t), stream));
-  const unsigned long long grid = (unsigned long long)cp.ngroups * (cp.ta + cp.tb);
-  if (grid == 0 || grid > 0x7fffffffULL) return fail(GENFFT_CUDA_ERR_SIZE, "chain grid of %llu tiles", grid);
-  ce->launch(cp, (unsigned)grid, stream);
+  ce->launch(cp, (unsigned)std::min(total, resident), stream);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
@@ -842,7 +854,7 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
   //     columns with p3 mod R1 in the class depend exactly on pass 2's tiles of that class.
   // Returns 1 if the pair was launched, 0 if the caller has to run the passes one by one, < 0 on error.
   const long long chain_target = (long long)env_int("GENFFT_CUDA_CHAIN_KB", 4096) << 10;
-  const long long chain_max = (long long)env_int("GENFFT_CUDA_CHAIN_MAX_KB", 32768) << 10;
+  const long long chain_max = (long long)env_int("GENFFT_CUDA_CHAIN_MAX_KB", 8192) << 10;
   const bool chain_on = env_int("GENFFT_CUDA_CHAIN", 1) != 0 && plan->grid_frac[0] >= 1.f && plan->grid_frac[1] >= 1.f &&
                         !env_int("GENFFT_CUDA_PERSISTENT", 0);
   auto try_chain = [&](size_t sa, size_t sb, bool three, long long units, int* rc_out) -> bool {
@@ -908,7 +920,7 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     cp.ta = cp.a.ntiles;
     cp.tb = cp.b.ntiles;
     if (!cp.ta || !cp.tb || !cp.ngroups) return false;
-    cp.lag = (uint32_t)std::min<long long>(std::max(1, env_int("GENFFT_CUDA_CHAIN_LAG", 2)), cp.ngroups);
+    cp.lag = (uint32_t)std::max(0, env_int("GENFFT_CUDA_CHAIN_LAG", 0));  // 0: chosen by launch_chain
     *rc_out = launch_chain(plan, ce, cp, stream);
     return *rc_out == GENFFT_CUDA_OK;
   };

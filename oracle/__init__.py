@@ -246,6 +246,13 @@ class Ref(_Lib):
                      argtypes=[_c.c_int, _c.c_long, _c.c_int, _c.c_int])
         return float(f(n, count, threads, int(fwd_only)))
 
+    def bench_c2c_array(self, n: int, count: int, threads: int, warm: int = 1, reps: int = 1) -> float:
+        """mean seconds per sweep over `count` distinct transforms, host array in -> host array out (DRAM-streaming)"""
+        f = self.lib.genfft_ref_bench_c2c_array_f32
+        f.restype = _c.c_double
+        f.argtypes = [_c.c_int, _c.c_long, _c.c_int, _c.c_int, _c.c_int]
+        return float(f(n, count, threads, warm, reps))
+
     def bench_r2c(self, n: int, count: int, threads: int) -> float:
         f = self.lib.genfft_ref_bench_r2c_f32
         f.restype = _c.c_double

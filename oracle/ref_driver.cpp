@@ -315,6 +315,43 @@ double genfft_ref_bench_c2c_f32(int n, long count, int threads, int fwd_only) {
   });
 }
 
+// The same transforms on a BATCH ARRAY held in host memory: `count` distinct length-n sequences in, `count` out, each
+// thread looping FFT<float>::transform over its contiguous share (the reference has no batch API, fft.h:80-85, so
+// this is what a caller of the CPU library does with the bench workload).  Unlike the fft_bench.cpp loop above,
+// whose single in/out buffer stays in L1/L2, the data streams from and to DRAM -- the same host-buffer-to-host-
+// buffer contract the CUDA library's host-pointer entry point is timed on.  Returns the wall time of the slowest
+// thread for one sweep over the array: mean over `reps` sweeps after `warm` untimed ones.
+double genfft_ref_bench_c2c_array_f32(int n, long count, int threads, int warm, int reps) {
+  if (!valid_pow2(n) || count < 1) return -1;
+  genfft::FFT<float> warm(n);
+  std::vector<cpx<float>> in((size_t)n * count), out((size_t)n * count);
+  {  // fill in parallel, untimed (one generator per thread)
+    std::vector<std::thread> pool;
+    const int nt = std::max(1, threads);
+    for (int t = 0; t < nt; t++)
+      pool.emplace_back([&, t] {
+        std::mt19937_64 rng(5489u + t);
+        std::uniform_real_distribution<float> dist(-1, 1);
+        const size_t lo = in.size() * t / nt, hi = in.size() * (t + 1) / nt;
+        for (size_t k = lo; k < hi; k++) in[k] = {dist(rng), dist(rng)};
+        for (size_t k = lo; k < hi; k++) out[k] = {0.f, 0.f};  // touch the pages
+      });
+    for (auto &th : pool) th.join();
+  }
+  reps = std::max(1, reps);
+  double sum = 0;
+  for (int r = -std::max(0, warm); r < reps; r++) {
+    double t = timed_parallel<float>(count, threads, [&](int, long lo, long hi) {
+      genfft::FFT<float> fft(n);
+      double t0 = now_s();
+      for (long k = lo; k < hi; k++) fft.transform<false>(out.data() + (size_t)k * n, in.data() + (size_t)k * n);
+      return now_s() - t0;
+    });
+    if (r >= 0) sum += t;
+  }
+  return sum / reps;
+}
+
 double genfft_ref_bench_c2c_f64(int n, long count, int threads, int fwd_only) {
   if (!valid_pow2(n)) return -1;
   genfft::FFT<double> warm(n);

@@ -132,8 +132,9 @@ def test_r2c_chain_is_bit_identical(lg, batch, half):
     with chain(True):
         l1 = run_counted(lambda: plan.forward(y1, x))
     assert torch.equal(y0, y1), plan.describe()
-    if lg >= 16:
-        assert l1 == l0 - 1, (l0, l1, plan.describe())
+    # whole transforms are the chain's groups here (the split pairs bins q and n/2 - q); above 8 MiB per transform
+    # they no longer sit in L2 between the passes and the plan runs its passes one by one
+    assert l1 == (l0 - 1 if n // 2 * 8 <= (8 << 20) else l0), (l0, l1, plan.describe())
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])

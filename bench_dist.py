@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--chunks", type=str, default="1,4")
     ap.add_argument("--fracs", type=str, default="0.7:0.3")
     ap.add_argument("--transports", type=str, default="nccl,p2p")
+    ap.add_argument("--phases", action="store_true", help="p2p: also report mean ms per phase (extra untimed pass)")
+    ap.add_argument("--barriers", type=str, default="flags", help="p2p transport: flags (peer memory) and/or collective")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -42,16 +44,17 @@ def main():
     for transport in args.transports.split(","):
         for transposed in (True, False):
             if transport == "nccl":
-                variants.append((transport, transposed, 1, 1.0, 1.0))
+                variants.append((transport, transposed, 1, 1.0, 1.0, "collective"))
             else:
                 for ch in [int(c) for c in args.chunks.split(",")]:
                     for fr in (args.fracs.split(",") if ch > 1 else ["1:1"]):
                         fl, frm = [float(v) for v in fr.split(":")]
-                        variants.append((transport, transposed, ch, fl, frm))
-    for transport, transposed, chunks, fl, frm in variants:
+                        for bar in args.barriers.split(","):
+                            variants.append((transport, transposed, ch, fl, frm, bar))
+    for transport, transposed, chunks, fl, frm, bar in variants:
         if True:
             plan = DistFFT2D(w, h, np.float32, transport=transport, transposed_out=transposed, chunks=chunks,
-                             frac_local=fl, frac_remote=frm)
+                             frac_local=fl, frac_remote=frm, barrier=bar)
             for _ in range(args.warmup):
                 plan.transform(slab)
             dist.barrier()
@@ -67,12 +70,23 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             ntr = 1 if transposed else 2
+            phases = None
+            if args.phases and transport == "p2p":
+                plan.start_phase_timing()
+                for _ in range(args.steps):
+                    plan.transform(slab)
+                ph = plan.phase_times_ms()
+                pt = torch.tensor(list(ph.values()), device="cuda", dtype=torch.float64)
+                pmax = pt.clone()
+                dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+                phases = {k: [round(float(a), 4), round(float(b), 4)] for k, a, b in zip(ph, pt.tolist(), pmax.tolist())}
             if rank == 0:
                 print(json.dumps({
                     "workload": f"C5: 2D C2C fp32 {w}x{h}, slab-decomposed over {world} GPUs", "transport": transport,
-                    "chunks": chunks, "frac_local": fl, "frac_remote": frm,
+                    "chunks": chunks, "frac_local": fl, "frac_remote": frm, "barrier": bar,
+                    "chain": os.environ.get("GENFFT_CUDA_CHAIN", "1"),
                     "output": "transposed (1 global transpose)" if transposed else "natural order (2 global transposes)",
-                    "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
+                    "phases_ms_rank0_and_max": phases, "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
                     "alltoall_bytes_sent_per_gpu_per_transpose": sent,
                     "nvlink_floor_ms_at_770GBs": ntr * sent / 770e9 * 1e3,
                     "nvlink_floor_ms_at_900GBs": ntr * sent / 900e9 * 1e3,

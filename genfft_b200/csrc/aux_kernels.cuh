@@ -223,4 +223,31 @@ __global__ void __launch_bounds__(256) copy_kernel(const __grid_constant__ CopyP
   }
 }
 
+// Cross-GPU barrier over peer memory (distributed 2D, p2p transport): every rank owns an array of `world` epoch
+// flags that all peers have mapped through CUDA IPC.  Thread r of the single CTA publishes this rank's arrival in
+// peer r's array, then waits until peer r's arrival shows up in the local array.  Stream order puts the kernel after
+// the pass whose NVLink stores it fences (a kernel boundary completes them system-wide) and before the pass that
+// reads what the peers stored, so a rank leaves the barrier only when every peer's earlier kernels are done --
+// in a few microseconds, without a collective library call on the critical path.
+struct PeerBarrierParams {
+  uint32_t* peer_flags[8];  // [kMaxPeers]: peer r's flag array (the own array at index `rank`)
+  int rank, world;
+  uint32_t epoch;  // strictly increasing per barrier
+};
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerBarrierParams p) {
+  const int r = threadIdx.x;
+  if (r >= p.world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[r] + p.rank), "r"(p.epoch) : "memory");
+  const uint32_t* mine = p.peer_flags[p.rank] + r;
+  uint32_t v, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - p.epoch) >= 0) break;
+    __nanosleep(100);
+    if (++spins > (1u << 27)) __trap();  // ~15 s: a peer that never arrives must fail loudly, never hang the GPU
+  }
+}
+
 }  // namespace genfft_cuda

@@ -1669,6 +1669,31 @@ int genfft_cuda_copy2d_dev(int precision, void* out, int64_t out_stride, int64_t
   return launch_copy(precision, cp, batch, (cudaStream_t)stream);
 }
 
+// Stream-ordered barrier across the ranks of a process group over IPC-mapped flag arrays (aux_kernels.cuh).
+int genfft_cuda_peer_barrier_dev(void* const* peer_flags, int rank, int world, uint32_t epoch, void* stream) {
+  if (!peer_flags || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(GENFFT_CUDA_ERR_ARG, "bad peer barrier arguments");
+  static_assert(sizeof(PeerBarrierParams{}.peer_flags) / sizeof(void*) == kMaxPeers, "flag arrays per barrier");
+  PeerBarrierParams p;
+  memset(&p, 0, sizeof p);
+  for (int r = 0; r < world; r++) {
+    if (!peer_flags[r]) return fail(GENFFT_CUDA_ERR_ARG, "null flag array");
+    p.peer_flags[r] = static_cast<uint32_t*>(peer_flags[r]);
+  }
+  p.rank = rank;
+  p.world = world;
+  p.epoch = epoch;
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
+int genfft_cuda_memset_dev(void* ptr, int value, size_t bytes) {
+  CU_TRY(cudaMemset(ptr, value, bytes));
+  return GENFFT_CUDA_OK;
+}
+
 int genfft_cuda_malloc(void** ptr, size_t bytes) {
   if (!ptr) return fail(GENFFT_CUDA_ERR_ARG, "null");
   cudaError_t e = cudaMalloc(ptr, bytes);

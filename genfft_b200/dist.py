@@ -229,7 +229,7 @@ class DistFFT2D:
 
     def __init__(self, width: int, height: int, dtype=np.float32, group=None, transport: str = "p2p",
                  transposed_out: bool = False, engine=None, chunks: int = 1, frac_local: float = 0.7,
-                 frac_remote: float = 0.3):
+                 frac_remote: float = 0.3, barrier: str = "flags"):
         if dist is None or not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.group = group
@@ -241,6 +241,8 @@ class DistFFT2D:
             raise ValueError("width and height must be divisible by the number of ranks")
         if transport not in ("p2p", "nccl"):
             raise ValueError("transport must be 'p2p' or 'nccl'")
+        if barrier not in ("flags", "collective"):
+            raise ValueError("barrier must be 'flags' or 'collective'")
         self.w, self.h = width, height
         self.hl, self.wp = height // self.world, width // self.world
         self.transport = transport
@@ -261,10 +263,25 @@ class DistFFT2D:
             self.final_buf = None if transposed_out else PeerBuffers(self.hl * self.w * esz, group)
             self.out = None if transposed_out else self.final_buf.tensor((self.hl, self.w), e.cdtype)
             self._token = torch.zeros(1, device="cuda")
+            # barrier between the passes: epoch flags in IPC-mapped peer memory (one tiny kernel, no collective call);
+            # "collective" keeps the all-reduce of a token (also what an injected CPU engine gets)
+            self._flags = None
+            if barrier == "flags" and engine is None:
+                self._flags = PeerBuffers(256, group)
+                check(lib().genfft_cuda_memset_dev(self._flags.local, 0, 256))
+                self._flag_ptrs = (C.c_void_p * self.world)(*self._flags.ptrs)
+                self._epoch = 0
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)  # every rank's flags are zeroed before anyone publishes an epoch
 
     def _stream_barrier(self):
         # stream-ordered cross-rank barrier: a rank leaves it only after every rank's earlier kernels on
         # this stream -- whose NVLink stores target our buffers -- have completed
+        if getattr(self, "_flags", None) is not None:
+            self._epoch += 1
+            check(lib().genfft_cuda_peer_barrier_dev(self._flag_ptrs, self.rank, self.world, self._epoch & 0xFFFFFFFF,
+                                                     torch.cuda.current_stream().cuda_stream))
+            return
         dist.all_reduce(self._token, group=self.group)
 
     def transform(self, in_slab, inv: bool = False):
@@ -281,18 +298,56 @@ class DistFFT2D:
             e.unpack(self.out, self.recv2)
             return self.out
         # p2p: stores go straight into the peers' buffers
+        mark = self._mark
+        mark()
         self._stream_barrier()  # peers finished reading their block / final buffers of the previous call
+        mark()
         e.rows_to_peers(in_slab, self.block_buf.ptrs, self.rank, inv)
+        mark()
         self._stream_barrier()
+        mark()
         if self.transposed_out:
             e.cols_ptr(self.block_out, self.block_buf.local, inv)
+            mark()
             return self.block_out
         e.cols_to_peers(self.block_buf.local, self.final_buf.ptrs, self.rank, inv)
+        mark()
         self._stream_barrier()
+        mark()
         return self.out
+
+    # optional per-phase timing of the p2p path (bench_dist.py --phases): CUDA events between the phases
+    phase_names = ("barrier0", "rows+transpose1", "barrier1", "cols+transpose2", "barrier2")
+    _events = None
+
+    def start_phase_timing(self):
+        self._events = []
+
+    def _mark(self):
+        if self._events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._events.append(ev)
+
+    def phase_times_ms(self):
+        """mean milliseconds per phase over the transforms recorded since start_phase_timing()"""
+        torch.cuda.synchronize()
+        ev, self._events = self._events, None
+        per = 5 if self.transposed_out else 6
+        n = len(ev) // per
+        out = [0.0] * (per - 1)
+        for k in range(n):
+            for j in range(per - 1):
+                out[j] += ev[k * per + j].elapsed_time(ev[k * per + j + 1]) / n
+        return dict(zip(self.phase_names, out))
 
     def close(self):
         if self.transport == "p2p":
+            if getattr(self, "_flags", None) is not None:
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)  # no peer is still spinning on (or about to write) our flags
+                self._flags.close()
+                self._flags = None
             self.block_buf.close()
             if self.final_buf is not None:
                 self.final_buf.close()

@@ -173,6 +173,13 @@ int genfft_cuda_copy2d_dev(int precision, void* out, int64_t out_stride, int64_t
                            int64_t in_stride, int64_t in_dist, int64_t rows, int64_t cols, int64_t batch,
                            void* stream);
 
+/* Stream-ordered barrier across the ranks of one node over IPC-mapped flag arrays: peer_flags[r] is rank r's array
+ * of `world` uint32 epochs (zero-initialised with genfft_cuda_memset_dev, mapped with the IPC helpers below); `epoch`
+ * must increase by one per barrier.  Replaces a collective-library call between the passes of the distributed 2D
+ * transform (nothing in the reference corresponds to it: genFFT has no multi-device code). */
+int genfft_cuda_peer_barrier_dev(void* const* peer_flags, int rank, int world, uint32_t epoch, void* stream);
+int genfft_cuda_memset_dev(void* ptr, int value, size_t bytes);
+
 /* CUDA IPC helpers so that ranks can map each other's receive buffers (cudaIpcMemHandle_t is 64 bytes). */
 int genfft_cuda_malloc(void** ptr, size_t bytes);
 int genfft_cuda_free(void* ptr);

@@ -31,11 +31,13 @@ def main():
         want_i = np.fft.ifft2(full.astype(np.complex128)) * (w * h)
         tol = (1e-6 if dt == np.float32 else 1e-14) * np.log2(w * h)
         slab = torch.from_numpy(full[rank * hl:(rank + 1) * hl].copy()).cuda()
-        for transport, chunks in (("nccl", 1), ("p2p", 1), ("p2p", 4)):
+        # p2p: peer-memory flag barrier (default) and the collective-call barrier
+        for transport, chunks, bar in (("nccl", 1, "collective"), ("p2p", 1, "flags"), ("p2p", 1, "collective"),
+                                       ("p2p", 4, "flags")):
             for transposed in (False, True):
                 if chunks > 1 and (w // world) // chunks < 32:
                     continue
-                plan = DistFFT2D(w, h, dt, transport=transport, transposed_out=transposed, chunks=chunks)
+                plan = DistFFT2D(w, h, dt, transport=transport, transposed_out=transposed, chunks=chunks, barrier=bar)
                 for inv, want in ((False, want_f), (True, want_i)):
                     for rep in range(2):  # twice: buffers are reused between calls
                         got = plan.transform(slab, inv)
@@ -46,7 +48,7 @@ def main():
                     ok = err <= tol
                     fails += not ok
                     if rank == 0 or not ok:
-                        print(f"[rank {rank}] {w}x{h} {dt.__name__} {transport} chunks={chunks} transposed={transposed} inv={inv}: "
+                        print(f"[rank {rank}] {w}x{h} {dt.__name__} {transport}/{bar} chunks={chunks} transposed={transposed} inv={inv}: "
                               f"rel-L2 {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
                 dist.barrier()
                 plan.close()

@@ -521,6 +521,18 @@ static PassParams emit_col(const PassSpec& ps, long long N, const void* in, long
   return p;
 }
 
+static bool strides_fit_32(const PassParams& p) {
+  auto fits = [](long long v) { return v >= 0 && v < (1LL << 32); };
+  return fits(p.in_stride_i) && fits(p.out_stride_k) && fits(p.tw_b_stride);
+}
+static void set_tile_divisors(PassParams& p) {
+  const FastDiv d1 = make_fast_div(p.n1), d2 = make_fast_div(p.n2);
+  p.n1_mul = d1.mul;
+  p.n1_shr = d1.shr;
+  p.n2_mul = d2.mul;
+  p.n2_shr = d2.shr;
+}
+
 static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p, cudaStream_t stream) {
   if (p.ntiles == 0) return GENFFT_CUDA_OK;
   int mode = p.mode;
@@ -532,6 +544,8 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
       ((uintptr_t)p.in % 16 == 0) && ((p.in_stride_c * (long long)elem_size(plan->precision)) % 16 == 0) &&
       p.ntiles >= 4u * (uint32_t)plan->num_sms)
     mode = M_ROWTMA;
+  // the compile-time modes address with 32-bit element strides (one multiply-add per access)
+  if (mode != M_GEN && !strides_fit_32(p)) mode = M_GEN;
   int rc = kernel_occupancy(ps.k, ps.k->func[mode][inv], ps.k->smem_mode[mode], plan->device, &occ);
   if (rc) return rc;
   // One-shot grids by default: the hardware block scheduler then balances the load dynamically, which on this part
@@ -543,15 +557,7 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
   if (frac) cap = std::max<long long>(1, (long long)(cap * p.grid_frac));
   const bool persistent = frac || env_int("GENFFT_CUDA_PERSISTENT", 0);
   PassParams q = p;
-  // Experimental (off): TMA staging of column tiles, one cp.async.bulk per 128-256-byte row.  Measured on B200 it
-  // LOSES badly (C3 294 -> 484 us, C5 10.7 -> 18.4 ms): the bulk-copy engine is not made for hundreds of tiny copies
-  // per tile; a tiled tensor map (cp.async.bulk.tensor, one instruction per tile) is the form to try next.
-  if ((mode == M_COL || mode == M_COLTW || mode == M_FIRST) && env_int("GENFFT_CUDA_TMA_COLS", 0)) {
-    const long long es = (long long)elem_size(plan->precision);
-    const bool aligned = ((uintptr_t)p.in % 16 == 0) && (p.in_stride_c == 1) && ((p.in_stride_i * es) % 16 == 0) &&
-                         ((p.in_t0 * es) % 16 == 0) && ((p.in_t1 * es) % 16 == 0) && ((ps.k->C * es) % 16 == 0);
-    q.tma_cols = (aligned && p.ncols % ps.k->C == 0 && num_stages(ps.k->L, ps.k->P) > 1) ? 1 : 0;
-  }
+  set_tile_divisors(q);
   int grid;
   if (persistent) {
     q.tiles_per_cta = 0;
@@ -917,6 +923,9 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     }
     const ChainEntry* ce = find_chain(plan->precision, ka, cp.a.mode, kb, cp.b.mode, inverse ? 1 : 0);
     if (!ce) return false;
+    if (!strides_fit_32(cp.a) || !strides_fit_32(cp.b)) return false;
+    set_tile_divisors(cp.a);
+    set_tile_divisors(cp.b);
     cp.ta = cp.a.ntiles;
     cp.tb = cp.b.ntiles;
     if (!cp.ta || !cp.tb || !cp.ngroups) return false;
@@ -1044,6 +1053,12 @@ int genfft_cuda_device_count(void) {
 }
 
 uint64_t genfft_cuda_launch_count(void) { return g_launches.load(); }
+
+// host evaluation of the kernels' division-free tile decode (tile_kernel.cuh: fast_div), for the CPU test suite
+uint32_t genfft_cuda_debug_fast_div(uint32_t x, uint32_t d) {
+  const FastDiv f = make_fast_div(d);
+  return fast_div(x, f.mul, f.shr);
+}
 
 int genfft_cuda_plan_c2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, int64_t batch, int64_t in_dist,
                             int64_t out_dist) {

@@ -43,8 +43,8 @@ struct PassParams {
   int mode;                  // host side only: which compiled addressing mode to launch (enum Mode)
   float grid_frac;           // host side only: fraction of the resident-CTA capacity to launch (0 = all)
   uint32_t tiles_per_cta;    // 0: grid-stride loop over tiles (persistent grid); K > 0: CTA b owns tiles [b*K, b*K+K)
-  int tma_cols;              // experimental, off by default (slower, see plan.cu): column modes stage the L x C input
-                             // tile with one cp.async.bulk per row into the exchange buffer, mbarrier-signalled
+  // tile -> (t0, t1, t2) without integer division: q = umulhi(x, mul) >> shr (mul == 0: divisor is 1), see fast_div()
+  uint32_t n1_mul, n1_shr, n2_mul, n2_shr;
   int inverse;               // conjugate on load and on store
   int in_real;               // 1: input is real scalars (imag = 0), FFT<T>::transform_real, fft.h:90-94
                              // 2: real part from `in`, imaginary part from `in2`, transform_interleave, fft.h:100-105
@@ -124,6 +124,30 @@ __host__ __device__ constexpr int tile_pitch_t(int L) { return pad_idx_t<PADSH>(
 //             real-FFT split, which couples bins q and M-q, is fused after the last butterfly stage
 enum Mode { M_GEN = 0, M_ROW = 1, M_COL = 2, M_COLTW = 3, M_FIRST = 4, M_ROWTMA = 5, M_ROWDIT = 6, M_COLTWDIT = 7 };
 
+// Division of a tile index (< 2^31) by a launch-invariant divisor d without the ~25-instruction software division:
+// host side  shr = ceil(log2 d) - 1, mul = ceil(2^(32 + shr) / d)  (d >= 2; mul = 0 encodes d == 1),
+// device side q = umulhi(x, mul) >> shr.  Exact for x < 2^31 (the usual round-up magic number; checked exhaustively
+// over the divisors the plans use in tests/test_abi.py through genfft_cuda_debug_fast_div).
+struct FastDiv {
+  uint32_t mul, shr;
+};
+inline FastDiv make_fast_div(uint32_t d) {
+  FastDiv f{0u, 0u};
+  if (d <= 1) return f;
+  uint32_t lg = 0;
+  while ((1ull << lg) < d) lg++;  // ceil(log2 d) >= 1
+  f.shr = lg - 1;
+  f.mul = (uint32_t)((((unsigned long long)1 << (32 + f.shr)) + d - 1) / d);
+  return f;
+}
+__host__ __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t mul, uint32_t shr) {
+#ifdef __CUDA_ARCH__
+  return mul ? (__umulhi(x, mul) >> shr) : x;
+#else
+  return mul ? (uint32_t)(((unsigned long long)x * mul) >> 32) >> shr : x;
+#endif
+}
+
 // ---- mbarrier / bulk-copy PTX (sm_90+; SASS: SYNCS / UBLKCP) ---------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -170,6 +194,58 @@ __device__ __forceinline__ void st_data(V* p, const V& v) {
   else *p = v;
 }
 
+// Strided global access  base[stride * k]  with the address formed by ONE instruction (IMAD.WIDE.U32 with an
+// immediate): `stride` is a 32-bit element stride, `k` a compile-time element count after unrolling.  Written in PTX
+// because the compiler otherwise strength-reduces the sixteen addresses of a tile column into chains of 64-bit
+// adds (2-3 instructions each); the access itself is PTX too so that it stays a global (not generic) access.
+template <typename V>
+__device__ __forceinline__ unsigned long long strided_addr(const V* base, uint32_t stride, uint32_t k) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(stride), "r"(k * (uint32_t)sizeof(V)), "l"(base));
+  return r;
+}
+template <int OP>
+__device__ __forceinline__ float2 ld_strided(const float2* base, uint32_t stride, uint32_t k) {
+  float2 v;
+  const unsigned long long a = strided_addr(base, stride, k);
+  if constexpr (OP == CO_STREAM) asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(a));
+  else if constexpr (OP == CO_L2ONLY) asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(a));
+  else asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(a));
+  return v;
+}
+template <int OP>
+__device__ __forceinline__ double2 ld_strided(const double2* base, uint32_t stride, uint32_t k) {
+  double2 v;
+  const unsigned long long a = strided_addr(base, stride, k);
+  if constexpr (OP == CO_STREAM) asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(a));
+  else if constexpr (OP == CO_L2ONLY) asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(a));
+  else asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(a));
+  return v;
+}
+template <int OP>
+__device__ __forceinline__ void st_strided(float2* base, uint32_t stride, uint32_t k, const float2& v) {
+  const unsigned long long a = strided_addr(base, stride, k);
+  if constexpr (OP == CO_STREAM) asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(a), "f"(v.x), "f"(v.y) : "memory");
+  else asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+template <int OP>
+__device__ __forceinline__ void st_strided(double2* base, uint32_t stride, uint32_t k, const double2& v) {
+  const unsigned long long a = strided_addr(base, stride, k);
+  if constexpr (OP == CO_STREAM) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(a), "d"(v.x), "d"(v.y) : "memory");
+  else asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+// read-only table entry (twiddles): non-coherent path
+__device__ __forceinline__ float2 ldg_strided(const float2* base, uint32_t stride, uint32_t k) {
+  float2 v;
+  asm("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(strided_addr(base, stride, k)));
+  return v;
+}
+__device__ __forceinline__ double2 ldg_strided(const double2* base, uint32_t stride, uint32_t k) {
+  double2 v;
+  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(strided_addr(base, stride, k)));
+  return v;
+}
+
 template <typename T, int L, int P, int C, int MODE, bool INV>
 struct TileKernel {
   static constexpr int TN = L / P;
@@ -187,11 +263,7 @@ struct TileKernel {
   static constexpr size_t XBUF_BYTES = (NST > 1 || DIT || PAIR) ? sizeof(cpx<T>) * (size_t)PITCH * C : 0;
   // TMA mode: [exchange buffer][input buffer C*L][mbarrier]
   static constexpr size_t INBUF_OFFSET = (XBUF_BYTES + 127) & ~(size_t)127;
-  static constexpr bool COLMODE = MODE == M_COL || MODE == M_COLTW || MODE == M_FIRST;
-  // column modes can stage their input tile by TMA into the exchange buffer itself (+ one mbarrier)
-  static constexpr size_t COLBAR_OFFSET = (XBUF_BYTES + 15) & ~(size_t)15;
-  static constexpr size_t SMEM_BYTES = TMA ? INBUF_OFFSET + sizeof(cpx<T>) * (size_t)L * C + 16
-                                           : (COLMODE && NST > 1 ? COLBAR_OFFSET + 16 : XBUF_BYTES);
+  static constexpr size_t SMEM_BYTES = TMA ? INBUF_OFFSET + sizeof(cpx<T>) * (size_t)L * C + 16 : XBUF_BYTES;
   static constexpr bool GEN = MODE == M_GEN;
   static constexpr bool UNIT_IN = ROWLIKE;
   static constexpr bool UNIT_OUT = ROWLIKE || MODE == M_FIRST;
@@ -214,10 +286,10 @@ struct TileKernel {
       t.p_base = 0;
       t.g_base = 0;
     } else {
-    uint32_t t2 = tile % prm.n2;
-    uint32_t t01 = tile / prm.n2;
-    uint32_t t1 = t01 % prm.n1;
-    uint32_t t0 = t01 / prm.n1;
+    const uint32_t t01 = fast_div(tile, prm.n2_mul, prm.n2_shr);
+    const uint32_t t2 = tile - t01 * prm.n2;
+    const uint32_t t0 = fast_div(t01, prm.n1_mul, prm.n1_shr);
+    const uint32_t t1 = t01 - t0 * prm.n1;
     t.col0 = t2 * C;
     t.in_off = (long long)t0 * prm.in_t0 + (long long)t1 * prm.in_t1;
     t.out_off = (long long)t0 * prm.out_t0 + (long long)t1 * prm.out_t1;
@@ -261,12 +333,10 @@ struct TileKernel {
     V al = __ldg(lo + (e & ((1u << prm.tw_shift) - 1u)));
     const cpx<T> a = cmul(cpx<T>(ah.x, ah.y), cpx<T>(al.x, al.y));  // W_M^(p*u)
     const V* tb = reinterpret_cast<const V*>(prm.tw_b) + p;
+    const uint32_t ts32 = (uint32_t)prm.tw_b_stride;
     V b[P];
 #pragma unroll
-    for (int i = 1; i < P; i++) {
-      tb += prm.tw_b_stride;
-      b[i] = __ldg(tb);
-    }
+    for (int i = 1; i < P; i++) b[i] = ldg_strided(tb, ts32, (uint32_t)i);
     x[0] = cmul(x[0], a);
 #pragma unroll
     for (int i = 1; i < P; i++) x[i] = cmul(x[i], cmul(a, cpx<T>(b[i].x, b[i].y)));
@@ -276,8 +346,11 @@ struct TileKernel {
   static __device__ __forceinline__ void load(const PassParams& prm, const Tile& t, int c, int u, cpx<T> (&x)[P]) {
     bool valid;
     const uint32_t col = column_of(prm, t, c, valid);
-    const long long base = t.in_off + (long long)col * prm.in_stride_c;
     if constexpr (!GEN) {
+      // Strides are below 2^32 elements here (launch_pass sends anything larger to M_GEN): every strided address is
+      // base + stride32 * constant.  (The branch around the loads is kept on purpose: without it ptxas hoists the
+      // later stages' twiddle loads to the top of the kernel and spills them.)
+      const long long base = t.in_off + (long long)col * prm.in_stride_c;
       if (valid) {
         if constexpr (UNIT_IN) {
           const V* src = reinterpret_cast<const V*>(prm.in) + base + u;
@@ -288,11 +361,10 @@ struct TileKernel {
           }
         } else {
           const V* src = reinterpret_cast<const V*>(prm.in) + base + (long long)u * prm.in_stride_i;
-          const long long step = (long long)TN * prm.in_stride_i;
+          const uint32_t s32 = (uint32_t)prm.in_stride_i;
 #pragma unroll
           for (int i = 0; i < P; i++) {
-            V v = ld_data<LDOP>(src);
-            src += step;
+            V v = ld_strided<LDOP>(src, s32, (uint32_t)(i * TN));
             x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
           }
         }
@@ -302,6 +374,7 @@ struct TileKernel {
       }
       if constexpr (MODE == M_COLTW || PAIR) apply_pass_twiddle(prm, t, col, u, x);
     } else {
+    const long long base = t.in_off + (long long)col * prm.in_stride_c;
 #pragma unroll
     for (int i = 0; i < P; i++) {
       const int idx = u + i * TN;
@@ -350,14 +423,13 @@ struct TileKernel {
         }
       } else {
         V* dst = reinterpret_cast<V*>(prm.out) + base + (long long)u * prm.out_stride_k;
-        const long long step = (long long)TN * prm.out_stride_k;
+        const uint32_t s32 = (uint32_t)prm.out_stride_k;
 #pragma unroll
         for (int i = 0; i < P; i++) {
           V v;
           v.x = x[i].x;
           v.y = INV ? -x[i].y : x[i].y;
-          st_data<STOP>(dst, v);
-          dst += step;
+          st_strided<STOP>(dst, s32, (uint32_t)(i * TN), v);
         }
       }
     } else {
@@ -680,46 +752,9 @@ struct TileKernel {
       const uint32_t K = prm.tiles_per_cta;
       const uint32_t step = K ? 1u : gridDim.x;
       const uint32_t tile_end = K ? min(prm.ntiles, (blockIdx.x + 1u) * K) : prm.ntiles;
-      uint64_t* colbar = nullptr;
-      uint32_t colparity = 0;
-      if constexpr (COLMODE && NST > 1) {
-        if (prm.tma_cols) {
-          colbar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem) + COLBAR_OFFSET);
-          if (tid == 0) {
-            mbar_init(colbar, 1);
-            fence_barrier_init();
-          }
-          __syncthreads();
-        }
-      }
       for (uint32_t tile = K ? blockIdx.x * K : blockIdx.x; tile < tile_end; tile += step) {
         Tile t = decode(prm, tile);
-        bool staged = false;
-        if constexpr (COLMODE && NST > 1) {
-          if (prm.tma_cols) {
-            // TMA-staged tile: row idx of the tile (C adjacent columns = one contiguous segment) -> smem[idx][0..C)
-            cpx<T>* inbuf = smem;
-            if (tid < 32) {
-              if (tid == 0) mbar_arrive_expect_tx(colbar, (uint32_t)(L * C * sizeof(cpx<T>)));
-              __syncwarp();
-              const V* gsrc = reinterpret_cast<const V*>(prm.in) + t.in_off + (long long)t.col0 * prm.in_stride_c;
-              for (int r = tid; r < L; r += 32)
-                bulk_load(inbuf + (size_t)r * C, gsrc + (long long)r * prm.in_stride_i, (uint32_t)(C * sizeof(cpx<T>)), colbar);
-            }
-            mbar_wait(colbar, colparity);
-            colparity ^= 1;
-            const V* src = reinterpret_cast<const V*>(inbuf) + (size_t)u_ld * C + c_ld;
-#pragma unroll
-            for (int i = 0; i < P; i++) {
-              V v = src[(size_t)i * TN * C];
-              x[i] = cpx<T>(v.x, INV ? -v.y : v.y);
-            }
-            __syncthreads();  // everyone holds its points: the buffer becomes the exchange buffer
-            if constexpr (MODE == M_COLTW) apply_pass_twiddle(prm, t, t.col0 + c_ld, u_ld, x);
-            staged = true;
-          }
-        }
-        if (!staged) load(prm, t, c_ld, u_ld, x);
+        load(prm, t, c_ld, u_ld, x);
         int c = c_ld, u = u_ld;
         run_stages<0>(prm, x, smem, c, u, c_st, u_st);
         if constexpr (DIT) {
@@ -730,8 +765,7 @@ struct TileKernel {
           __syncthreads();
         } else {
           store(prm, t, c, u, x);
-          if (colbar) fence_proxy_async();  // generic-proxy accesses of the buffer before the next tile's TMA writes
-          if (NST > 1) __syncthreads();     // next tile's first scatter must not overtake this tile's gathers
+          if (NST > 1) __syncthreads();  // next tile's first scatter must not overtake this tile's gathers
         }
       }
     }

@@ -173,6 +173,10 @@ int genfft_cuda_copy2d_dev(int precision, void* out, int64_t out_stride, int64_t
                            int64_t in_stride, int64_t in_dist, int64_t rows, int64_t cols, int64_t batch,
                            void* stream);
 
+/* Test hook: x / d as the kernels compute it when they decode a tile index (magic-number multiply, exact for
+ * x < 2^31); host code only. */
+uint32_t genfft_cuda_debug_fast_div(uint32_t x, uint32_t d);
+
 /* Stream-ordered barrier across the ranks of one node over IPC-mapped flag arrays: peer_flags[r] is rank r's array
  * of `world` uint32 epochs (zero-initialised with genfft_cuda_memset_dev, mapped with the IPC helpers below); `epoch`
  * must increase by one per barrier.  Replaces a collective-library call between the passes of the distributed 2D

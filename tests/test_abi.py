@@ -100,3 +100,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "genfft_ref" not in text and "oracle/" not in text, f
+
+
+def test_tile_decode_division_is_exact():
+    """the kernels decode tile -> (t0, t1, t2) with a magic-number multiply instead of an integer division
+    (tile_kernel.cuh: fast_div); it must be exact for every tile index below 2^31 and every divisor a plan can
+    produce (tile counts per row / block: powers of two, powers of two plus one for the pair tiles, batch counts)"""
+    import random
+    import genfft_b200 as g
+    f = g.lib().genfft_cuda_debug_fast_div
+    rng = random.Random(7)
+    divisors = set(range(1, 1100)) | {(1 << k) + o for k in range(1, 31) for o in (-1, 0, 1)} | \
+        {rng.randrange(1, 1 << 31) for _ in range(300)}
+    divisors = {d for d in divisors if 1 <= d < (1 << 31)}
+    top = (1 << 31) - 1
+    for d in sorted(divisors):
+        xs = {0, 1, d - 1, d, d + 1, top, top - 1, top // d * d, max(0, top // d * d - 1)}
+        xs |= {rng.randrange(0, top + 1) for _ in range(40)}
+        xs |= {min(top, k * d + o) for k in (2, 3, 1000, 65535, 65536) for o in (-1, 0, 1)}
+        for x in xs:
+            if 0 <= x <= top:
+                assert f(x, d) == x // d, (x, d)

@@ -16,6 +16,7 @@
 //     stores), fusing the all-to-all transpose into the producing pass.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include "radix.cuh"
 
 namespace genfft_cuda {
@@ -566,33 +567,39 @@ struct TileKernel {
     if (col >= (uint32_t)prm.ncols) return;
     V* dst = reinterpret_cast<V*>(prm.out) + (long long)col * prm.out_stride_c;
     const V* tw = reinterpret_cast<const V*>(prm.dit_tw);
+    auto bins = [&](auto full) {  // two copies of the loop: the half-spectrum one carries no mirror-store code
 #pragma unroll
-    for (int i = 0; i < P; i++) {
-      const int k = u + i * TN;
-      const int kp = (L - k) & (L - 1);
-      const V zp = sm[pad_idx(kp)];
-      const V w = __ldg(tw + k);
-      const T er = (x[i].x + zp.x) * T(0.5), ei = (x[i].y - zp.y) * T(0.5);
-      const T orr = (x[i].x - zp.x) * T(0.5), oi = (x[i].y + zp.y) * T(0.5);
-      const T tr = -w.y, ti = w.x;
-      V f;
-      f.x = er - (tr * orr - ti * oi);
-      f.y = ei - (tr * oi + ti * orr);
-      if (k == 0) {
-        f.y = T(0);  // exactly real, as in the reference (F[0] = zeroval)
-        V nyq;
-        nyq.x = x[i].x - x[i].y;
-        nyq.y = T(0);
-        dst[L] = nyq;
+      for (int i = 0; i < P; i++) {
+        const int k = u + i * TN;
+        const int kp = (L - k) & (L - 1);
+        const V zp = sm[pad_idx(kp)];
+        const V w = __ldg(tw + k);
+        const T er = (x[i].x + zp.x) * T(0.5), ei = (x[i].y - zp.y) * T(0.5);
+        const T orr = (x[i].x - zp.x) * T(0.5), oi = (x[i].y + zp.y) * T(0.5);
+        const T tr = -w.y, ti = w.x;
+        V f;
+        f.x = er - (tr * orr - ti * oi);
+        f.y = ei - (tr * oi + ti * orr);
+        if (k == 0) {
+          f.y = T(0);  // exactly real, as in the reference (F[0] = zeroval)
+          V nyq;
+          nyq.x = x[i].x - x[i].y;
+          nyq.y = T(0);
+          dst[L] = nyq;
+        }
+        dst[k] = f;
+        if constexpr (decltype(full)::value) {
+          if (k != 0) {
+            V g;
+            g.x = f.x;
+            g.y = -f.y;
+            dst[2 * L - k] = g;
+          }
+        }
       }
-      dst[k] = f;
-      if (!prm.dit_half && k != 0) {
-        V g;
-        g.x = f.x;
-        g.y = -f.y;
-        dst[2 * L - k] = g;
-      }
-    }
+    };
+    if (prm.dit_half) bins(std::false_type());
+    else bins(std::true_type());
   }
 
   // ---- fused real-FFT split for the last pass of a multi-pass transform (see M_COLTWDIT) ----
@@ -624,20 +631,58 @@ struct TileKernel {
     const cpx<T> a(av.x, av.y);
     const V* tw = reinterpret_cast<const V*>(prm.dit_tw);
     const long long M = (long long)Ns * L;
-#pragma unroll
-    for (int i = 0; i < P; i++) {
-      const int k = u + i * TN;
-      const int kp = (p == 0) ? ((L - k) & (L - 1)) : (L - 1 - k);
-      const V zp = smp[pad_idx(kp)];
-      const V bv = __ldg(tw + k);
-      const cpx<T> w = cmul(a, cpx<T>(bv.x, bv.y));  // W_n^q
-      const T er = (x[i].x + zp.x) * T(0.5), ei = (x[i].y - zp.y) * T(0.5);
-      const T orr = (x[i].x - zp.x) * T(0.5), oi = (x[i].y + zp.y) * T(0.5);
+    // the split of one bin: X[q] = E - t O with the partner bin zp = Z[M - q] and w = W_n^q
+    auto split = [](const cpx<T>& z, const V& zp, const cpx<T>& w) {
+      const T er = (z.x + zp.x) * T(0.5), ei = (z.y - zp.y) * T(0.5);
+      const T orr = (z.x - zp.x) * T(0.5), oi = (z.y + zp.y) * T(0.5);
       const T tr = -w.y, ti = w.x;
       V f;
       f.x = er - (tr * orr - ti * oi);
       f.y = ei - (tr * oi + ti * orr);
-      const long long q = (long long)p + (long long)k * Ns;
+      return f;
+    };
+    if (p != 0) {
+      // Every column but the self-paired column 0 (one lane of one tile per transform): q = p + k Ns is never 0, the
+      // partner index is L-1-k, and all addresses of the thread's 16 bins are a base plus a multiple of a fixed
+      // step -- the output with a 32-bit stride (Ns < 2^32), the twiddles and the partner slots with immediates.
+      const V* twu = tw + u;
+      const V* smu = smp + pad_idx(L - 1 - u);
+      V* dq = dst + p + (long long)u * Ns;
+      V* dm = dst + (2 * M - p - (long long)u * Ns);
+      auto bins = [&](auto full) {  // two copies of the loop: the half-spectrum one carries no mirror-store code
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+          V zp;
+          if constexpr (TN >= PADN) {
+            zp = *(smu - i * (TN + TN / PADN));  // pad_idx(L-1-u - i*TN) = pad_idx(L-1-u) - i*(TN + TN/PADN)
+          } else {
+            zp = smp[pad_idx(L - 1 - u - i * TN)];
+          }
+          const V bv = __ldg(twu + i * TN);
+          const cpx<T> w = cmul(a, cpx<T>(bv.x, bv.y));  // W_n^q
+          const V f = split(x[i], zp, w);
+          st_strided<CO_DEFAULT>(dq, Ns, (uint32_t)(i * TN), f);
+          if constexpr (decltype(full)::value) {
+            V g;
+            g.x = f.x;
+            g.y = -f.y;
+            *(dm - (long long)Ns * (i * TN)) = g;
+          }
+        }
+      };
+      if (prm.dit_half) bins(std::false_type());
+      else bins(std::true_type());
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const int k = u + i * TN;
+      const int kp = (L - k) & (L - 1);
+      const V zp = smp[pad_idx(kp)];
+      const V bv = __ldg(tw + k);
+      const cpx<T> w = cmul(a, cpx<T>(bv.x, bv.y));  // W_n^q
+      V f = split(x[i], zp, w);
+      const long long q = (long long)k * Ns;
       if (q == 0) {
         f.y = T(0);
         V nyq;

@@ -323,7 +323,7 @@ double genfft_ref_bench_c2c_f32(int n, long count, int threads, int fwd_only) {
 // thread for one sweep over the array: mean over `reps` sweeps after `warm` untimed ones.
 double genfft_ref_bench_c2c_array_f32(int n, long count, int threads, int warm, int reps) {
   if (!valid_pow2(n) || count < 1) return -1;
-  genfft::FFT<float> warm(n);
+  genfft::FFT<float> keep_plan(n);  // holds the per-N singleton alive across the sweeps
   std::vector<cpx<float>> in((size_t)n * count), out((size_t)n * count);
   {  // fill in parallel, untimed (one generator per thread)
     std::vector<std::thread> pool;

@@ -397,6 +397,29 @@ class RealFFT2D(_Plan):
             check(lib().genfft_cuda_exec_r2c_2d(self._h, o.ptr, out_stride, i.ptr, in_stride))
         return out
 
+    def forward_2x(self, out, in1, in2, out_stride: int | None = None, in_stride1: int | None = None,
+                   in_stride2: int | None = None):
+        """RealFFT2D<T>::forward_2x(out, out_stride, in1, in_stride1, in2, in_stride2) (FFTReal.h:106-118): the
+        spectrum of in1 + i*in2, two real images in one complex 2D transform."""
+        self._need()
+        out_stride = self._w if out_stride is None else out_stride
+        in_stride1 = self._w if in_stride1 is None else in_stride1
+        in_stride2 = self._w if in_stride2 is None else in_stride2
+        o, i1 = _pair(out, in1, self.precision)
+        i2 = _Buf(in2)
+        if i2.cuda != o.cuda or i2.precision != self.precision:
+            raise ValueError("in2 must match in1")
+        if (o.nscalars < 2 * ((self._hgt - 1) * out_stride + self._w)
+                or i1.nscalars < (self._hgt - 1) * in_stride1 + self._w
+                or i2.nscalars < (self._hgt - 1) * in_stride2 + self._w):
+            raise ValueError("buffer too small for height x width with the given stride")
+        if o.cuda:
+            check(lib().genfft_cuda_exec_r2c_2d_2x_dev(self._h, o.ptr, out_stride, i1.ptr, in_stride1, i2.ptr,
+                                                       in_stride2, _stream()))
+        else:
+            check(lib().genfft_cuda_exec_r2c_2d_2x(self._h, o.ptr, out_stride, i1.ptr, in_stride1, i2.ptr, in_stride2))
+        return out
+
 
 def launch_count() -> int:
     return int(lib().genfft_cuda_launch_count())

@@ -201,7 +201,9 @@ struct CopyParams {
   void* out;
   long long in_stride, out_stride, in_dist, out_dist;
   long long rows, cols;
-  int in_real;  // widen real scalars to complex
+  int in_real;  // 1: widen real scalars to complex; 2: real part from `in`, imaginary part from `in2` (forward_2x)
+  const void* in2;
+  long long in2_stride;
 };
 
 template <typename T>
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) copy_kernel(const __grid_constant__ CopyP
       V v;
       if (p.in_real) {
         v.x = reinterpret_cast<const T*>(p.in)[b * p.in_dist + r * p.in_stride + c];
-        v.y = T(0);
+        v.y = p.in_real == 2 ? reinterpret_cast<const T*>(p.in2)[r * p.in2_stride + c] : T(0);
       } else {
         v = reinterpret_cast<const V*>(p.in)[b * p.in_dist + r * p.in_stride + c];
       }

@@ -160,6 +160,34 @@ int genfft_cuda_exec_r2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stri
   return GENFFT_CUDA_OK;
 }
 
+// RealFFT2D<T>::forward_2x(out, out_stride, in1, in_stride1, in2, in_stride2) (FFTReal.h:106-118): host pointers.
+// Both images are staged densely, so the device side always takes the path that reads them without interleaving.
+int genfft_cuda_exec_r2c_2d_2x(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in1,
+                               int64_t in_stride1, const void* in2, int64_t in_stride2) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_R2C_2D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  if (!out || !in1 || !in2) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out_stride < p->width || in_stride1 < p->width || in_stride2 < p->width)
+    return set_error(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
+  const size_t es = elem_size(p->precision);
+  const size_t img_bytes = ((size_t)p->width * p->height * es / 2 + 255) & ~(size_t)255;
+  const size_t out_bytes = (size_t)p->width * p->height * es;
+  int rc = ensure_stage(p, 2 * img_bytes, out_bytes);
+  if (rc) return rc;
+  cudaStream_t st = p->streams[0];
+  char* d1 = (char*)p->stage_in;
+  char* d2 = d1 + img_bytes;
+  const size_t row = p->width * es / 2;
+  HX_TRY(cudaMemcpy2DAsync(d1, row, in1, in_stride1 * es / 2, row, p->height, cudaMemcpyHostToDevice, st));
+  HX_TRY(cudaMemcpy2DAsync(d2, row, in2, in_stride2 * es / 2, row, p->height, cudaMemcpyHostToDevice, st));
+  rc = genfft_cuda_exec_r2c_2d_2x_dev(plan, p->stage_out, p->width, d1, p->width, d2, p->width, st);
+  if (rc) return rc;
+  HX_TRY(cudaMemcpy2DAsync(out, out_stride * es, p->stage_out, p->width * es, p->width * es, p->height,
+                           cudaMemcpyDeviceToHost, st));
+  HX_TRY(cudaStreamSynchronize(st));
+  return GENFFT_CUDA_OK;
+}
+
 // half-spectrum inverse on host pointers
 int genfft_cuda_exec_c2r(genfft_cuda_plan_t plan, void* out, const void* in) {
   Plan* p = plan;

@@ -1346,6 +1346,21 @@ int genfft_cuda_separate_2x_real_dev(int precision, void* out1, void* out2, cons
   return GENFFT_CUDA_OK;
 }
 
+// plan-owned device staging of the device-pointer entry points that need a dense temporary
+static int ensure_aux(Plan* p, size_t need) {
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (p->aux_bytes >= need) return GENFFT_CUDA_OK;
+  if (p->aux) {
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaFree(p->aux));
+    p->aux = nullptr;
+    p->aux_bytes = 0;
+  }
+  if (cudaMalloc(&p->aux, need) != cudaSuccess) return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc(%zu) failed", need);
+  p->aux_bytes = need;
+  return GENFFT_CUDA_OK;
+}
+
 int genfft_cuda_plan_r2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t width, int64_t height) {
   if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
   if (!is_pow2(width) || !is_pow2(height) || width > kMaxN || height > kMaxN || width < 2)
@@ -1362,6 +1377,7 @@ int genfft_cuda_plan_r2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t wid
   p->out_dist = width;
   rc = setup_r2c_tables(p, precision, width);
   if (!rc) rc = build_seq(&p->seq_v, p->device, precision, height, true);
+  if (!rc) rc = build_seq(&p->seq_h, p->device, precision, width, false);  // forward_2x: full-width complex rows
   if (rc) {
     delete p;
     return rc;
@@ -1408,6 +1424,52 @@ int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_
   return GENFFT_CUDA_OK;
 }
 
+// RealFFT2D<T>::forward_2x (include/genFFT/FFTReal.h:106-118): the 2D transform of the complex image in1 + i*in2,
+// i.e. two real images at the price of one complex transform.  The reference builds the rows with
+// scramble_row_x2 (:167-180: every row is transform_interleave of a row of in1 and a row of in2; the offset of in2's
+// second half is written with in_stride1 there -- a typo, in_stride2 is what is meant and what is done here) and
+// finishes with the column transform on all `width` columns.  Here: the rows' first pass reads its real and imaginary
+// parts from the two images (no interleaved copy is materialised) when both have the same row stride; otherwise, or
+// with GENFFT_CUDA_2X_FUSED=0, one interleaving copy into plan-owned memory precedes the ordinary 2D pass chain.
+int genfft_cuda_exec_r2c_2d_2x_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in1,
+                                   int64_t in_stride1, const void* in2, int64_t in_stride2, void* stream) {
+  Plan* p = plan;
+  if (!p || p->kind != PLAN_R2C_2D) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  if (!out || !in1 || !in2) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (out == in1 || out == in2) return fail(GENFFT_CUDA_ERR_ARG, "RealFFT2D::forward_2x requires out != in");
+  if (out_stride < p->width || in_stride1 < p->width || in_stride2 < p->width)
+    return fail(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t elems = (size_t)p->width * p->height;
+  const bool fused = in_stride1 == in_stride2 && env_int("GENFFT_CUDA_2X_FUSED", 1);
+  std::vector<Step> steps, cols;
+  seq_steps(p->seq_h, false, steps, false, fused);
+  seq_steps(p->seq_v, true, cols, false, false);
+  steps.insert(steps.end(), cols.begin(), cols.end());
+  View vout{out, out_stride};
+  if (fused) {
+    View vin{const_cast<void*>(in1), in_stride1};  // pitch in real scalars (the first pass reads scalars)
+    return run_chain(p, steps, vin, vout, p->width, elems, p->height, p->width, 0, st, nullptr, nullptr, in2);
+  }
+  int rc = ensure_aux(p, elems * elem_size(p->precision));
+  if (rc) return rc;
+  CopyParams cp;
+  memset(&cp, 0, sizeof cp);
+  cp.in = in1;
+  cp.in2 = in2;
+  cp.out = p->aux;
+  cp.rows = p->height;
+  cp.cols = p->width;
+  cp.in_stride = in_stride1;
+  cp.in2_stride = in_stride2;
+  cp.out_stride = p->width;
+  cp.in_real = 2;
+  rc = launch_copy(p->precision, cp, 1, st);
+  if (rc) return rc;
+  View vin{p->aux, p->width};
+  return run_chain(p, steps, vin, vout, p->width, elems, p->height, p->width, 0, st);
+}
+
 int genfft_cuda_plan_c2r_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, int64_t batch, int64_t in_dist,
                             int64_t out_dist) {
   if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
@@ -1447,18 +1509,8 @@ int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in,
   const size_t es = elem_size(p->precision);
   // stage the pre-processed spectrum Z' (M complex per transform) in plan-owned memory
   {
-    std::lock_guard<std::mutex> lk(p->mu);
-    const size_t need = (size_t)M * p->batch * es;
-    if (p->aux_bytes < need) {
-      if (p->aux) {
-        CU_TRY(cudaDeviceSynchronize());
-        CU_TRY(cudaFree(p->aux));
-        p->aux = nullptr;
-        p->aux_bytes = 0;
-      }
-      if (cudaMalloc(&p->aux, need) != cudaSuccess) return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc(%zu) failed", need);
-      p->aux_bytes = need;
-    }
+    int rc = ensure_aux(p, (size_t)M * p->batch * es);
+    if (rc) return rc;
   }
   C2rParams cp;
   memset(&cp, 0, sizeof cp);

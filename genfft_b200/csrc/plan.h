@@ -41,6 +41,7 @@ struct Plan {
   float grid_frac[2] = {1.f, 1.f};  // share of the resident-CTA capacity: {all passes but the last, last pass}
   Seq seq;    // 1D sequence (c2c_1d: n; r2c: n/2; 2d: rows (width); vert: n)
   Seq seq_v;  // 2D: columns (height)
+  Seq seq_h;  // r2c_2d: full-width complex rows (RealFFT2D::forward_2x)
   // DIT twiddles (W_n two-level)
   const void* dit_hi = nullptr;
   const void* dit_lo = nullptr;

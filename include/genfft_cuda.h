@@ -110,6 +110,12 @@ int genfft_cuda_separate_2x_real_dev(int precision, void* out1, void* out2, cons
  * width x height complex spectrum; out_stride in complex elements, in_stride in real scalars; out != in. */
 int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
                                 int64_t in_stride, void* stream);
+/* RealFFT2D<T>::forward_2x(out, out_stride, in1, in_stride1, in2, in_stride2) (FFTReal.h:106-118): full
+ * width x height spectrum of the complex image in1 + i*in2 (two real images in one transform); strides of the inputs
+ * in real scalars.  The reference offsets in2's lower half with in_stride1 (FFTReal.h:178), a typo: in_stride2 is
+ * honoured here. */
+int genfft_cuda_exec_r2c_2d_2x_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in1,
+                                   int64_t in_stride1, const void* in2, int64_t in_stride2, void* stream);
 /* inverse of RealFFT<T>::forward(half = true), unscaled; out != in; n >= 2. */
 int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream);
 /* RealFFT<T>::forward(out, in, half) (FFTReal.h:204-213); half is fixed at plan time.  `out` is also the
@@ -137,6 +143,8 @@ int genfft_cuda_exec_r2c(genfft_cuda_plan_t plan, void* out, const void* in);
 int genfft_cuda_exec_c2r(genfft_cuda_plan_t plan, void* out, const void* in);
 int genfft_cuda_exec_c2c_interleave(genfft_cuda_plan_t plan, void* out, const void* in1, const void* in2);
 int genfft_cuda_exec_r2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in, int64_t in_stride);
+int genfft_cuda_exec_r2c_2d_2x(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in1,
+                               int64_t in_stride1, const void* in2, int64_t in_stride2);
 int genfft_cuda_exec_c2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,
                             int64_t in_stride, int inverse);
 int genfft_cuda_exec_vert(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in,

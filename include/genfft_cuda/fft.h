@@ -259,6 +259,18 @@ class RealFFT2D {
     detail::check(genfft_cuda_exec_r2c_2d_dev(impl.get(), d_out, out_stride, d_in, in_stride, stream));
   }
 
+  ///@brief Forward transform of two real images at once: the spectrum of in1 + i*in2 (FFTReal.h:106-118)
+  ///@param in_stride1 stride, in scalar elements, of the 1st input array
+  ///@param in_stride2 stride, in scalar elements, of the 2nd input array
+  void forward_2x(std::complex<T>* out, int out_stride, const T* in1, int in_stride1, const T* in2, int in_stride2) {
+    detail::check(genfft_cuda_exec_r2c_2d_2x(impl.get(), out, out_stride, in1, in_stride1, in2, in_stride2));
+  }
+  void forward_2x_dev(void* d_out, int out_stride, const void* d_in1, int in_stride1, const void* d_in2,
+                      int in_stride2, void* stream = nullptr) {
+    detail::check(genfft_cuda_exec_r2c_2d_2x_dev(impl.get(), d_out, out_stride, d_in1, in_stride1, d_in2, in_stride2,
+                                                 stream));
+  }
+
   int cols() const { return impl ? w : 0; }
   int rows() const { return impl ? h : 0; }
 

@@ -235,6 +235,17 @@ class Ref(_Lib):
             raise ValueError("real_fft2d rejected size")
         return out
 
+    def real_fft2d_2x(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """RealFFT2D<T>::forward_2x (FFTReal.h:114-118) with equal input strides; a, b are (height, width) real."""
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        h, w = a.shape
+        out = np.zeros((h, w), dtype=_CPX[a.dtype])
+        f = self._fn("real_fft2d_2x", a.dtype,
+                     argtypes=[_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int])
+        if f(_ptr(out), w, _ptr(a), _ptr(b), w, w, h):
+            raise ValueError("real_fft2d_2x rejected size")
+        return out
+
     # ---- CPU-baseline timing (restated test/fft_bench.cpp loops; seconds inside transform calls) ----
     def bench_c2c(self, n: int, count: int, threads: int, dtype=np.float32, fwd_only: bool = True) -> float:
         if n > (1 << 23):

@@ -138,6 +138,16 @@ int real_fft2d(T *out, int out_stride, const T *in, int in_stride, int width, in
   return 0;
 }
 
+// RealFFT2D<T>::forward_2x (FFTReal.h:114-118).  Its row recursion offsets the lower half of in2 with in_stride1
+// (FFTReal.h:178), so the reference is only meaningful for in_stride1 == in_stride2; the driver passes one stride.
+template <class T>
+int real_fft2d_2x(T *out, int out_stride, const T *in1, const T *in2, int in_stride, int width, int height) {
+  if (!valid_pow2(width) || !valid_pow2(height)) return 1;
+  genfft::RealFFT2D<T> fft(width, height);
+  fft.forward_2x((cpx<T> *)out, out_stride, in1, in_stride, in2, in_stride);
+  return 0;
+}
+
 double now_s() {
   using clk = std::chrono::steady_clock;
   return std::chrono::duration<double>(clk::now().time_since_epoch()).count();
@@ -209,6 +219,12 @@ int genfft_ref_real_fft2d_f32(float *out, int os, const float *in, int is, int w
 }
 int genfft_ref_real_fft2d_f64(double *out, int os, const double *in, int is, int w, int h) {
   return real_fft2d<double>(out, os, in, is, w, h);
+}
+int genfft_ref_real_fft2d_2x_f32(float *out, int os, const float *in1, const float *in2, int is, int w, int h) {
+  return real_fft2d_2x<float>(out, os, in1, in2, is, w, h);
+}
+int genfft_ref_real_fft2d_2x_f64(double *out, int os, const double *in1, const double *in2, int is, int w, int h) {
+  return real_fft2d_2x<double>(out, os, in1, in2, is, w, h);
 }
 // FFT::transform_real / transform_interleave + separate_2x_real_FFT (fft.h:90-105, FFTReal.h:35-66)
 int genfft_ref_transform_real_f32(float *out, const float *in, int n) {

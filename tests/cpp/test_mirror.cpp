@@ -218,8 +218,37 @@ void test_real_fft2d(int w, int h) {
   for (size_t i = 0; i < in.size(); i++) CHECK(std::abs(cd(out[i]) - ref[i]) <= eps * 1.5, "real 2d %dx%d i=%zu", w, h, i);
 }
 
+// forward_2x (FFTReal.h:106-118): spectrum of in1 + i*in2, with different strides of the two images
+template <class T>
+void test_real_fft2d_2x(int w, int h) {
+  genfft::RealFFT2D<T> fft(w, h);
+  const int s1 = w + 2, s2 = w + 4;
+  std::vector<T> in1((size_t)s1 * h), in2((size_t)s2 * h);
+  dummy(in1);
+  dummy(in2);
+  std::vector<std::complex<T>> out((size_t)w * h);
+  fft.forward_2x(out.data(), w, in1.data(), s1, in2.data(), s2);
+  std::vector<cd> ref((size_t)w * h);
+  for (int r = 0; r < h; r++) {
+    std::vector<cd> row(w);
+    for (int c = 0; c < w; c++) row[c] = cd(in1[(size_t)r * s1 + c], in2[(size_t)r * s2 + c]);
+    fft_rec(row, false);
+    std::copy(row.begin(), row.end(), ref.begin() + (size_t)r * w);
+  }
+  for (int c = 0; c < w; c++) {
+    std::vector<cd> col(h);
+    for (int r = 0; r < h; r++) col[r] = ref[(size_t)r * w + c];
+    fft_rec(col, false);
+    for (int r = 0; r < h; r++) ref[(size_t)r * w + c] = col[r];
+  }
+  const double eps = fft_eps<T>(w * h);
+  for (size_t i = 0; i < out.size(); i++) CHECK(std::abs(cd(out[i]) - ref[i]) <= eps * 2, "real 2d 2x %dx%d i=%zu", w, h, i);
+}
+
 int main() {
   test_real_fft2d<float>(64, 32);
+  test_real_fft2d_2x<float>(64, 32);
+  test_real_fft2d_2x<double>(16, 128);
   test_real_fft2d<double>(16, 128);
   genfft::FFT<float> empty;
   CHECK(!(bool)empty && empty.size() == 0, "default-constructed plan must be empty");

@@ -268,6 +268,61 @@ def test_real_fft2d_vs_reference(checkers, dt, w, h):
     assert oracle.rel_l2(h_out[:, :w], got) <= 1e-6
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("w,h", [(2, 1), (2, 2), (4, 2), (8, 8), (64, 16), (16, 256), (1024, 64), (256, 4096),
+                                 (32768, 4), (16384, 16)])
+def test_real_fft2d_forward_2x(checkers, monkeypatch, fused, dt, w, h):
+    """RealFFT2D::forward_2x (FFTReal.h:106-118): the spectrum of in1 + i*in2.  Untested in the reference; pinned
+    against the compiled reference (equal strides -- its row recursion mixes the strides up otherwise, :178) and
+    against numpy's fft2.  Both device paths: real/imaginary parts read from the two images by the first pass
+    (GENFFT_CUDA_2X_FUSED=1) and the interleaving copy."""
+    monkeypatch.setenv("GENFFT_CUDA_2X_FUSED", fused)
+    rng = np.random.default_rng(3 * w + h)
+    a = rng.uniform(-1, 1, (h, w)).astype(dt)
+    b = rng.uniform(-1, 1, (h, w)).astype(dt)
+    want = np.fft.fft2(a.astype(np.float64) + 1j * b.astype(np.float64))
+    plan = g.RealFFT2D(w, h, dt)
+    d_out = torch.full((h, w), FILL, dtype=TCPX[dt], device="cuda")
+    plan.forward_2x(d_out, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    got = d_out.cpu().numpy()
+    assert oracle.rel_l2(got, want) <= oracle.tolerance(w * h, dt)
+    ref = checkers[0]
+    if ref is not None:
+        assert oracle.rel_l2(got, ref.real_fft2d_2x(a, b)) <= oracle.tolerance(w * h, dt)
+    # the two real spectra come apart with the Hermitian split, as after transform_interleave
+    fa = np.fft.fft2(a.astype(np.float64))
+    gm = np.conj(np.roll(np.roll(got[::-1, ::-1], 1, axis=0), 1, axis=1))  # conj(G[-ky, -kx])
+    assert oracle.rel_l2((got + gm) / 2, fa) <= oracle.tolerance(w * h, dt)
+    # unequal, padded strides on device pointers (always correct here; the reference's typo makes it unusable)
+    pa = torch.zeros((h, w + 2), dtype=torch.from_numpy(a).dtype, device="cuda")
+    pb = torch.zeros((h, w + 6), dtype=pa.dtype, device="cuda")
+    pa[:, :w] = torch.from_numpy(a).cuda()
+    pb[:, :w] = torch.from_numpy(b).cuda()
+    d_pad = torch.full((h, w + 1), FILL, dtype=TCPX[dt], device="cuda")
+    plan.forward_2x(d_pad, pa, pb, out_stride=w + 1, in_stride1=w + 2, in_stride2=w + 6)
+    got_pad = d_pad.cpu().numpy()
+    assert oracle.rel_l2(got_pad[:, :w], got) <= 1e-6
+    assert np.all(got_pad[:, w:] == FILL)
+    # host pointers
+    h_out = np.empty((h, w), dtype=CPX[dt])
+    plan.forward_2x(h_out, a, b)
+    assert oracle.rel_l2(h_out, got) <= 1e-6
+
+
+def test_real_fft2d_forward_2x_errors():
+    plan = g.RealFFT2D(8, 4, np.float32)
+    a = torch.zeros((4, 8), device="cuda")
+    out = torch.zeros((4, 8), dtype=torch.complex64, device="cuda")
+    with pytest.raises(g.GenfftCudaError):
+        plan.forward_2x(out, a, a, in_stride1=4)  # stride smaller than the width
+    with pytest.raises(ValueError):
+        plan.forward_2x(out, a, torch.zeros((2, 8), device="cuda"))  # second image too small
+    wrong = g.FFT2D(8, 4)  # a c2c_2d plan is not an r2c_2d plan
+    assert g.lib().genfft_cuda_exec_r2c_2d_2x_dev(wrong._h, out.data_ptr(), 8, a.data_ptr(), 8, a.data_ptr(), 8, None) != 0
+    assert g.lib().genfft_cuda_exec_r2c_2d_2x_dev(plan._h, out.data_ptr(), 8, a.data_ptr(), 8, None, 8, None) != 0
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n,batch", [(2, 3), (4, 1), (8, 2), (64, 5), (4096, 3), (1 << 15, 2), (1 << 17, 2), (1 << 20, 1)])
 def test_half_spectrum_inverse(dt, n, batch):

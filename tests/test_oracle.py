@@ -189,3 +189,20 @@ def test_reference_2pow24_hook(ref):
     rng = np.random.default_rng(3)
     x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n))
     assert oracle.rel_l2(ref.c2c(x), np.fft.fft(x)) <= 1e-14
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_reference_real_fft2d_matches_numpy(checkers, dt):
+    """RealFFT2D::forward and forward_2x (FFTReal.h:83-118) have no test in the reference: pin the compiled
+    reference's outputs (the comparands of the GPU parity tests) against numpy's fft2."""
+    ref = checkers[0]
+    if ref is None:
+        pytest.skip("compiled reference not present")
+    for w, h in [(4, 2), (8, 8), (64, 16), (16, 128), (512, 32)]:
+        rng = np.random.default_rng(w * 31 + h)
+        a = rng.uniform(-1, 1, (h, w)).astype(dt)
+        b = rng.uniform(-1, 1, (h, w)).astype(dt)
+        tol = oracle.tolerance(w * h, dt)
+        assert oracle.rel_l2(ref.real_fft2d(a), np.fft.fft2(a.astype(np.float64))) <= tol
+        want = np.fft.fft2(a.astype(np.float64) + 1j * b.astype(np.float64))
+        assert oracle.rel_l2(ref.real_fft2d_2x(a, b), want) <= tol

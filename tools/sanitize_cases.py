@@ -25,6 +25,6 @@ for dt, cd in ((np.float32, torch.complex64), (np.float64, torch.complex128)):
     x = torch.randn(256, 37, dtype=cd, device="cuda"); y = torch.empty_like(x); g.FFTVert(256, dt).transform(y, x, 37)
     x = torch.randn(8192, 40, dtype=cd, device="cuda"); y = torch.empty_like(x); g.FFTVert(8192, dt).transform(y, x, 40)
     x = torch.randn(512, 1024, dtype=cd, device="cuda"); y = torch.empty_like(x); g.FFT2D(1024, 512, dt).transform(y, x)
-    r = torch.randn(64, 256, dtype=rd, device="cuda"); y = torch.empty(64, 256, dtype=cd, device="cuda"); g.RealFFT2D(256, 64, dt).forward(y, r)
+    r = torch.randn(64, 256, dtype=rd, device="cuda"); y = torch.empty(64, 256, dtype=cd, device="cuda"); g.RealFFT2D(256, 64, dt).forward(y, r); g.RealFFT2D(256, 64, dt).forward_2x(y, r, r.clone())
 torch.cuda.synchronize()
 print("cases done")

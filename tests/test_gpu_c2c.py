@@ -58,6 +58,37 @@ def test_c2c_pow2_vs_reference(comparand, checkers, dt, lg):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_reference_test_harness_acceptance(checkers, dt):
+    """The reference's own acceptance run on the CUDA path: TestFFT_Pow2 and TestRealFFT_Pow2
+    (test/fft_test_impl.h:35-58,84-106) compare against reference_impl::FFT_pow2 (test/fft_ref_impl.h:90-96) with
+    the absolute FFT_Eps (test/test_util.h:62-72) over the size loops of test/test_fft.cpp:41-66 and
+    test/test_real_fft.cpp:42-67.  FFT_pow2 accumulates its angles, so in double it is only usable as a comparand
+    up to 2^12; float runs the reference's full loop."""
+    ref = checkers[0]
+    if ref is None:
+        pytest.skip("compiled reference (with its test harness) not present")
+    for lg in range(1, 17 if dt == np.float32 else 13):
+        n = 1 << lg
+        eps = fft_eps(n, dt)
+        x = ref.dummy_complex(n, dt)
+        want = ref.testref_fft_pow2(x)
+        got, _ = gpu_c2c(x)
+        assert np.max(np.abs(got.real - want.real)) <= eps and np.max(np.abs(got.imag - want.imag)) <= eps, n
+        back, _ = gpu_c2c(got, True)
+        assert np.max(np.abs(back.real / n - x.real)) <= eps and np.max(np.abs(back.imag / n - x.imag)) <= eps, n
+        r = ref.dummy_real(n, dt)
+        want_r = ref.testref_fft_pow2(r.astype(x.dtype))
+        for half in (True, False):
+            lim = n // 2 + 1 if half else n
+            out = torch.full((n,), 43 + 21j, dtype=torch.complex64 if dt == np.float32 else torch.complex128,
+                             device="cuda")
+            g.RealFFT(n, dt, half=half).forward(out, torch.from_numpy(r).cuda(), half)
+            got_r = out.cpu().numpy()
+            assert np.max(np.abs(got_r[:lim] - want_r[:lim])) <= eps * 1.5, (n, half)
+            assert np.all(got_r[lim:] == 43 + 21j), "Corruption detected"  # test/fft_test_impl.h:102-105
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n,batch", [(2, 5), (16, 300), (64, 33), (256, 17), (1024, 9), (4096, 64), (4096, 7),
                                      (8192, 3), (1 << 15, 3), (1 << 17, 2)])
 def test_c2c_batched(comparand, dt, n, batch):

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgenfft_cuda.so")
+# GENFFT_CUDA_LIB selects another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("GENFFT_CUDA_LIB") or os.path.join(HERE, "lib", "libgenfft_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "genfft_cuda.h")
 
 F32, F64 = 0, 1

@@ -2,8 +2,8 @@
 # Builds genfft_b200/lib/libgenfft_cuda.so for sm_100a (in-tree, so the .so travels to the GPU box).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../lib"
-OBJ="$HERE/../lib/obj"
+OUT="${GENFFT_LIB_OUT:-$HERE/../lib}"  # GENFFT_LIB_OUT + GENFFT_NVCC_EXTRA: variant builds for A/B measurements
+OBJ="$OUT/obj"
 mkdir -p "$OUT" "$OBJ"
 NVCC=${NVCC:-nvcc}
 FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $GENFFT_NVCC_EXTRA"

@@ -821,7 +821,13 @@ struct TileKernel {
 // thread's 16 complex points alone are 64 registers
 template <typename T, int THREADS>
 constexpr int min_blocks() {
-  constexpr int target = sizeof(T) == 4 ? 1024 : 512;
+#ifndef GENFFT_F64_TARGET_THREADS
+#define GENFFT_F64_TARGET_THREADS 512
+#endif
+#ifndef GENFFT_F32_TARGET_THREADS
+#define GENFFT_F32_TARGET_THREADS 1024
+#endif
+  constexpr int target = sizeof(T) == 4 ? GENFFT_F32_TARGET_THREADS : GENFFT_F64_TARGET_THREADS;
   return THREADS >= target ? 1 : target / THREADS;
 }
 

@@ -1,0 +1,31 @@
+"""Scratch: A/B timing of compile-time variants of libgenfft_cuda in one process.
+usage: python tools/variant_bench.py <lib_dir>[,<lib_dir>...] <config>...   (lib_dir relative to genfft_b200/, e.g. lib,lib_exp_a)"""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import genfft_b200 as g
+from genfft_b200 import _lib
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import quick_bench as q
+
+libs = sys.argv[1].split(",")
+which = sys.argv[2:]
+for name in libs:
+    _lib._lib = None
+    _lib.LIB_PATH = os.path.join(ROOT, "genfft_b200", name, "libgenfft_cuda.so")
+    print(f"== {name}", flush=True)
+    if "c3" in which:
+        q.c2c(1 << 24, 1, np.float64)
+        q.c2c(1 << 20, 16, np.float64)
+        q.c2c(4096, 1 << 15, np.float64)
+    if "c3f" in which:
+        q.c2c(1 << 24, 1, np.float32)
+        q.c2c(1 << 21, 256, np.float32)
+    if "c4" in which:
+        q.r2c(1 << 22, 256)
+    if "c5" in which:
+        q.fft2d(32768, 32768)
+    if "c2" in which:
+        q.c2c(4096, 1 << 16)
+    torch.cuda.empty_cache()

@@ -3,6 +3,16 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import genfft_b200 as g
+if "2x" in sys.argv[1:]:  # only RealFFT2D::forward_2x: first pass reading two images (1 and 2 row passes), and the copy path
+    for dt, cd in ((np.float32, torch.complex64), (np.float64, torch.complex128)):
+        rd = torch.float32 if dt == np.float32 else torch.float64
+        for w, h in ((256, 64), (32768, 4), (16, 256)):
+            a = torch.randn(h, w, dtype=rd, device="cuda"); b = torch.randn(h, w + 2, dtype=rd, device="cuda")
+            y = torch.empty(h, w, dtype=cd, device="cuda"); p = g.RealFFT2D(w, h, dt)
+            p.forward_2x(y, a, a.clone()); p.forward_2x(y, a, b, in_stride2=w + 2)
+    torch.cuda.synchronize()
+    print("2x cases done")
+    sys.exit(0)
 for dt, cd in ((np.float32, torch.complex64), (np.float64, torch.complex128)):
     rd = torch.float32 if dt == np.float32 else torch.float64
     # M_ROW / M_ROWTMA (needs >= 4 tiles per SM)

@@ -27,6 +27,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OUT = sys.stdout  # replaced by claim_stdout() in main()
 N_FFT = 4096
 BATCH = 1 << 16
 METRIC = "effective GFLOP/s (5N*log2N/t), batched 1D C2C fp32 N=4096 x 2^16 per GPU"
@@ -111,6 +112,15 @@ class ClockSampler:
                 "reasons": sorted(seen)}
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    the box sets NCCL_DEBUG), so fd 1 is pointed at stderr for the run and the line goes to the saved real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def reference_arm(args, rank: int, world: int) -> int:
     """genFFT's own CPU implementation of the path on the host cores (oracle/_ref), same metric/config."""
     if rank != 0:
@@ -120,7 +130,8 @@ def reference_arm(args, rank: int, world: int) -> int:
         if os.path.isdir(oracle.REFERENCE_ROOT):
             oracle.build("ref")
     if not oracle.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgenfft_ref.so was not built"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgenfft_ref.so was not built"}), file=OUT,
+              flush=True)
         return 0
     ref = oracle.Ref()
     threads = ref.hardware_threads()
@@ -150,7 +161,7 @@ def reference_arm(args, rank: int, world: int) -> int:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_build": ref.describe(),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
     return 0
 
 
@@ -169,6 +180,8 @@ def main() -> int:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    global OUT
+    OUT = claim_stdout()
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 
@@ -304,7 +317,7 @@ def main() -> int:
                                     "sample": f"unavailable: {e}"}
         if not args.no_extras:
             line["extras"] = extras(g, np, torch)
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

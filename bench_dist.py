@@ -16,7 +16,48 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from genfft_b200.dist import DistFFT2D  # noqa: E402
+from genfft_b200.dist import DistFFT1D, DistFFT2D, four_step_shape  # noqa: E402
+
+
+def bench_one_d(args, rank, world):
+    """One large 1D C2C transform (four-step over the slab decomposition): n = 2^args.one_d points, fp32."""
+    n = 1 << args.one_d
+    h, w = four_step_shape(n, world)
+    gen = torch.Generator(device="cuda").manual_seed(rank)
+    shard = torch.view_as_complex(torch.rand((n // world, 2), generator=gen, device="cuda") * 2 - 1)
+    flop = 5.0 * n * math.log2(n)
+    sent = (n * 8 / world) * (world - 1) / world
+    for transport in args.transports.split(","):
+        for transposed in (True, False):
+            plan = DistFFT1D(n, np.float32, transport=transport, transposed_out=transposed)
+            for _ in range(args.warmup):
+                plan.transform(shard)
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                plan.transform(shard)
+            b.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / args.steps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            ntr = 2 if transposed else 3
+            if rank == 0:
+                print(json.dumps({
+                    "workload": f"1D C2C fp32 n=2^{args.one_d} ({h} x {w} four-step), slab-decomposed over {world} GPUs",
+                    "transport": transport, "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
+                    "output": f"transposed Z[kr][kc] = X[kr + {h} kc] (2 global transposes)" if transposed
+                              else "natural order (3 global transposes)",
+                    "alltoall_bytes_sent_per_gpu_per_transpose": sent,
+                    "nvlink_floor_ms_at_770GBs": ntr * sent / 770e9 * 1e3,
+                    "frac_of_nvlink_roofline_770": (ntr * sent / 770e9 * 1e3) / ms if world > 1 else None,
+                }), flush=True)
+            plan.close()
+            del plan
+            torch.cuda.empty_cache()
 
 
 def main():
@@ -29,11 +70,16 @@ def main():
     ap.add_argument("--transports", type=str, default="nccl,p2p")
     ap.add_argument("--phases", action="store_true", help="p2p: also report mean ms per phase (extra untimed pass)")
     ap.add_argument("--barriers", type=str, default="flags", help="p2p transport: flags (peer memory) and/or collective")
+    ap.add_argument("--one-d", type=int, default=0, help="instead of C5: one 1D transform of 2^ONE_D points (DistFFT1D)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    if args.one_d:
+        bench_one_d(args, rank, world)
+        dist.destroy_process_group()
+        return
     w = h = args.size
     hl = h // world
     gen = torch.Generator(device="cuda").manual_seed(rank)

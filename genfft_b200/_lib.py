@@ -80,6 +80,8 @@ _SIGNATURES = {
     "genfft_cuda_plan_dist_cols": (C.c_int, [_plan_p, C.c_int, _i64, _i64, C.c_int]),
     "genfft_cuda_exec_dist_cols_dev": (C.c_int, [_vp, _vp, C.POINTER(_vp), _i64, _i64, _vp, _i64, C.c_int, _vp]),
     "genfft_cuda_copy2d_dev": (C.c_int, [C.c_int, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "genfft_cuda_twiddle2d_dev": (C.c_int, [C.c_int, _vp, _i64, _i64, _i64, _i64, _i64, C.c_int, _vp]),
+    "genfft_cuda_transpose_dev": (C.c_int, [C.c_int, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "genfft_cuda_debug_fast_div": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "genfft_cuda_peer_barrier_dev": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint32, _vp]),
     "genfft_cuda_memset_dev": (C.c_int, [_vp, C.c_int, C.c_size_t]),

@@ -225,6 +225,77 @@ __global__ void __launch_bounds__(256) copy_kernel(const __grid_constant__ CopyP
   }
 }
 
+// Inter-step twiddle of the distributed four-step 1D transform (N = H*W points seen as an H x W row-major matrix whose
+// row slabs live on different GPUs): after the length-H column transforms, element (kr, c) is multiplied by
+// W_N^(kr*c) before the length-W row transforms.  In place on a (rows x cols) slab whose first row is global row row0.
+struct Twiddle2dParams {
+  void* data;
+  long long stride;  // complex elements between rows
+  long long rows, cols, row0;
+  const void* tw_hi;  // two-level table of W_N^e = (cos, -sin)(2*pi*e/N)
+  const void* tw_lo;
+  int tw_shift;
+  int inverse;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) twiddle2d_kernel(const __grid_constant__ Twiddle2dParams p) {
+  using V = typename vec2<T>::type;
+  V* d = reinterpret_cast<V*>(p.data);
+  const unsigned long long lo_mask = (1ull << p.tw_shift) - 1ull;
+  for (long long r = blockIdx.y; r < p.rows; r += gridDim.y) {
+    const unsigned long long kr = (unsigned long long)(p.row0 + r);
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < p.cols;
+         c += (long long)gridDim.x * blockDim.x) {
+      const unsigned long long e = kr * (unsigned long long)c;  // < H*W = N
+      const V wh = __ldg(reinterpret_cast<const V*>(p.tw_hi) + (e >> p.tw_shift));
+      const V wl = __ldg(reinterpret_cast<const V*>(p.tw_lo) + (e & lo_mask));
+      cpx<T> w = cmul(cpx<T>(wh.x, wh.y), cpx<T>(wl.x, wl.y));
+      if (p.inverse) w.y = -w.y;
+      const V v = d[r * p.stride + c];
+      const cpx<T> z = cmul(cpx<T>(v.x, v.y), w);
+      V o;
+      o.x = z.x;
+      o.y = z.y;
+      d[r * p.stride + c] = o;
+    }
+  }
+}
+
+// out[c*out_stride + r] = in[r*in_stride + c]: 32 x 32 tiles through padded shared memory, both sides coalesced.
+// Last step of the distributed four-step 1D transform when the result is wanted in natural order.
+struct TransposeParams {
+  const void* in;
+  void* out;
+  long long in_stride, out_stride;
+  long long rows, cols;  // of `in`
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ TransposeParams p) {
+  using V = typename vec2<T>::type;
+  __shared__ V tile[32][33];
+  const V* in = reinterpret_cast<const V*>(p.in);
+  V* out = reinterpret_cast<V*>(p.out);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  const long long tiles_c = (p.cols + 31) / 32, tiles_r = (p.rows + 31) / 32;
+  for (long long t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const long long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const long long r = r0 + ty + j, c = c0 + tx;
+      if (r < p.rows && c < p.cols) tile[ty + j][tx] = in[r * p.in_stride + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const long long c = c0 + ty + j, r = r0 + tx;
+      if (r < p.rows && c < p.cols) out[c * p.out_stride + r] = tile[tx][ty + j];
+    }
+    __syncthreads();
+  }
+}
+
 // Cross-GPU barrier over peer memory (distributed 2D, p2p transport): every rank owns an array of `world` epoch
 // flags that all peers have mapped through CUDA IPC.  Thread r of the single CTA publishes this rank's arrival in
 // peer r's array, then waits until peer r's arrival shows up in the local array.  Stream order puts the kernel after

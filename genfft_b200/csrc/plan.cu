@@ -1736,6 +1736,66 @@ int genfft_cuda_copy2d_dev(int precision, void* out, int64_t out_stride, int64_t
   return launch_copy(precision, cp, batch, (cudaStream_t)stream);
 }
 
+// data[r][c] *= W_N^((row0 + r) * c), conjugated for the inverse: the twiddle between the column and the row transforms
+// of the distributed four-step 1D transform (genfft_b200/dist.py::DistFFT1D).  n_total = N = H * W.
+int genfft_cuda_twiddle2d_dev(int precision, void* data, int64_t stride, int64_t rows, int64_t cols, int64_t row0,
+                              int64_t n_total, int inverse, void* stream) {
+  if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return fail(GENFFT_CUDA_ERR_ARG, "bad precision");
+  if (!data) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (rows < 0 || cols < 0 || row0 < 0 || stride < cols) return fail(GENFFT_CUDA_ERR_ARG, "bad rows/cols/stride");
+  if (!is_pow2(n_total) || n_total < 8 || n_total > (1LL << 40))
+    return fail(GENFFT_CUDA_ERR_SIZE, "n_total must be a power of two in [8, 2^40]");
+  if (cols > n_total || row0 + rows > n_total / std::max<int64_t>(cols, 1))  // exponents (row0 + r) * c stay below N
+    return fail(GENFFT_CUDA_ERR_SIZE, "(row0 + rows) * cols exceeds n_total");
+  if (!rows || !cols) return GENFFT_CUDA_OK;
+  int dev, sms;
+  int rc = usable_device(&dev, &sms);
+  if (rc) return rc;
+  Twiddle2dParams tp;
+  memset(&tp, 0, sizeof tp);
+  rc = two_level_table(dev, precision, n_total, &tp.tw_hi, &tp.tw_lo, &tp.tw_shift);
+  if (rc) return rc;
+  tp.data = data;
+  tp.stride = stride;
+  tp.rows = rows;
+  tp.cols = cols;
+  tp.row0 = row0;
+  tp.inverse = inverse ? 1 : 0;
+  dim3 grid((unsigned)std::min<long long>((cols + 255) / 256, 1024), (unsigned)std::min<long long>(rows, 65535));
+  if (precision == GENFFT_CUDA_F32)
+    twiddle2d_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+  else
+    twiddle2d_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
+// out[c * out_stride + r] = in[r * in_stride + c] (complex elements); out != in.
+int genfft_cuda_transpose_dev(int precision, void* out, int64_t out_stride, const void* in, int64_t in_stride,
+                              int64_t rows, int64_t cols, void* stream) {
+  if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return fail(GENFFT_CUDA_ERR_ARG, "bad precision");
+  if (!out || !in || out == in) return fail(GENFFT_CUDA_ERR_ARG, "null or aliased buffer");
+  if (rows < 0 || cols < 0 || in_stride < cols || out_stride < rows) return fail(GENFFT_CUDA_ERR_ARG, "bad rows/cols/stride");
+  if (!rows || !cols) return GENFFT_CUDA_OK;
+  TransposeParams tp;
+  tp.in = in;
+  tp.out = out;
+  tp.in_stride = in_stride;
+  tp.out_stride = out_stride;
+  tp.rows = rows;
+  tp.cols = cols;
+  const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  const unsigned grid = (unsigned)std::min<long long>(tiles, 1LL << 20);
+  if (precision == GENFFT_CUDA_F32)
+    transpose_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+  else
+    transpose_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
 // Stream-ordered barrier across the ranks of a process group over IPC-mapped flag arrays (aux_kernels.cuh).
 int genfft_cuda_peer_barrier_dev(void* const* peer_flags, int rank, int world, uint32_t epoch, void* stream) {
   if (!peer_flags || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)

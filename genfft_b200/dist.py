@@ -86,7 +86,8 @@ class CudaSlabEngine:
 
     def __del__(self):
         try:
-            for h in [self._rows, self._cols] + [x for pair in self._chunk_plans for x in pair]:
+            plain = getattr(self, "_rows_plain", None)
+            for h in [self._rows, self._cols, plain] + [x for pair in self._chunk_plans for x in pair]:
                 if h:
                     lib().genfft_cuda_plan_destroy(h)
         except Exception:
@@ -163,6 +164,37 @@ class CudaSlabEngine:
     def cols_ptr(self, out, block_ptr: int, inv: bool):
         check(lib().genfft_cuda_exec_dist_cols_dev(self._cols, out.data_ptr(), None, self.wp, 0, block_ptr, self.wp,
                                                    int(inv), self._stream()))
+
+
+    # -- distributed four-step 1D (DistFFT1D): copies, twiddle, plain row transforms, final transpose ----------
+    def pack_cols(self, send, slab):
+        """send[g, r, :] = slab[r, g*Wp:(g+1)*Wp] (per-destination column blocks of a row slab)."""
+        check(lib().genfft_cuda_copy2d_dev(self.precision, send.data_ptr(), self.wp, self.hl * self.wp, slab.data_ptr(),
+                                           self.w, self.wp, self.hl, self.wp, self.p, self._stream()))
+
+    def cols_blocks_to_peers(self, slab, peer_ptrs, rank: int):
+        """The same blocks stored straight into the peers' (H x W/P) block buffers at rows [rank*H/P, ...)."""
+        for g in range(self.p):
+            check(lib().genfft_cuda_copy2d_dev(self.precision, peer_ptrs[g] + rank * self.hl * self.wp * self.esize,
+                                               self.wp, 0, slab.data_ptr() + g * self.wp * self.esize, self.w, 0,
+                                               self.hl, self.wp, 1, self._stream()))
+
+    def twiddle(self, slab, row0: int, inv: bool):
+        """slab[r, c] *= W_N^((row0 + r) * c), N = H*W (conjugated for the inverse), in place."""
+        check(lib().genfft_cuda_twiddle2d_dev(self.precision, slab.data_ptr(), self.w, self.hl, self.w, row0,
+                                              self.w * self.h, int(inv), self._stream()))
+
+    def rows(self, out, slab, inv: bool):
+        """out[r] = FFT of slab[r] (H/P contiguous rows of length W)."""
+        if getattr(self, "_rows_plain", None) is None:
+            self._rows_plain = C.c_void_p()
+            check(lib().genfft_cuda_plan_c2c_1d(C.byref(self._rows_plain), self.precision, self.w, self.hl, 0, 0))
+        check(lib().genfft_cuda_exec_c2c_dev(self._rows_plain, out.data_ptr(), slab.data_ptr(), int(inv), self._stream()))
+
+    def transpose(self, out, block):
+        """out (W/P x H) = block (H x W/P) transposed."""
+        check(lib().genfft_cuda_transpose_dev(self.precision, out.data_ptr(), self.h, block.data_ptr(), self.wp, self.h,
+                                              self.wp, self._stream()))
 
 
 class _PtrView:
@@ -351,3 +383,124 @@ class DistFFT2D:
             self.block_buf.close()
             if self.final_buf is not None:
                 self.final_buf.close()
+
+
+def four_step_shape(n: int, world: int) -> tuple[int, int]:
+    """(H, W) with H * W = n, H <= W, both divisible by `world`: the matrix view of the distributed 1D transform."""
+    if not _is_pow2(n) or not _is_pow2(world):
+        raise ValueError("n and the number of ranks must be powers of two")
+    lg = n.bit_length() - 1
+    h = 1 << (lg // 2)
+    w = n // h
+    if h < 2 or h % world or w % world or n < 8:
+        raise ValueError(f"n = {n} is too small to split over {world} ranks (needs H = 2^floor(log2(n)/2) >= ranks)")
+    return h, w
+
+
+class DistFFT1D:
+    """genfft::FFT<T>(n) (fft.h:54-113) for one LARGE transform spread over a process group: the four-step algorithm
+    on the slab decomposition.  The n = H*W points are an H x W row-major matrix x[r*W + c]; rank g holds rows
+    [g*H/P, (g+1)*H/P), i.e. its contiguous n/P input points.  With k = kr + H*kc:
+
+        X[kr + H*kc] = sum_c W_W^(c*kc) * W_n^(c*kr) * sum_r W_H^(r*kr) x[r*W + c]
+
+    1. global transpose 1: every rank gets the (H x W/P) column block of its columns c;
+    2. length-H column transforms on that block, the result scattered back to row slabs (global transpose 2);
+    3. twiddle W_n^(kr*c) on the (H/P x W) slab;
+    4. length-W row transforms; the slab now holds Z[kr][kc] = X[kr + H*kc]  (``transposed_out=True`` stops here);
+    5. natural order: global transpose 3 (fused into the row transforms' stores) + a local (H x W/P) transpose,
+       after which rank g holds X[g*n/P : (g+1)*n/P].
+
+    Transports as in DistFFT2D: ``"p2p"`` stores into IPC-mapped peer buffers from the kernels (the column / row
+    transforms' stores are transposes 2 and 3; transpose 1 is a strided peer copy), ``"nccl"`` packs, calls
+    ``all_to_all_single`` and unpacks.  Unscaled inverse with ``inv=True``, as FFT<T>::transform<true>.
+    """
+
+    def __init__(self, n: int, dtype=np.float32, group=None, transport: str = "p2p", transposed_out: bool = False,
+                 engine=None, barrier: str = "flags"):
+        if dist is None or not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if transport not in ("p2p", "nccl"):
+            raise ValueError("transport must be 'p2p' or 'nccl'")
+        if barrier not in ("flags", "collective"):
+            raise ValueError("barrier must be 'flags' or 'collective'")
+        self.n = n
+        self.h, self.w = four_step_shape(n, self.world)
+        self.hl, self.wp = self.h // self.world, self.w // self.world
+        self.transport = transport
+        self.transposed_out = transposed_out
+        self.engine = engine if engine is not None else CudaSlabEngine(self.w, self.h, self.world, dtype)
+        e = self.engine
+        self.out = e.empty(self.hl, self.w) if transposed_out else e.empty(self.wp, self.h)
+        if transport == "nccl":
+            self.send = e.empty(self.world, self.hl, self.wp)
+            self.block = e.empty(self.h, self.wp)
+            self.block_out = e.empty(self.h, self.wp)
+            self.recv2 = e.empty(self.world, self.hl, self.wp)
+            self.slab = e.empty(self.hl, self.w)
+        else:
+            esz = 8 if e.cdtype == torch.complex64 else 16
+            self.block_buf = PeerBuffers(self.h * self.wp * esz, group)
+            self.slab_buf = PeerBuffers(self.hl * self.w * esz, group)
+            self.block = self.block_buf.tensor((self.h, self.wp), e.cdtype)
+            self.slab = self.slab_buf.tensor((self.hl, self.w), e.cdtype)
+            self._token = torch.zeros(1, device="cuda")
+            self._flags = None
+            if barrier == "flags" and engine is None:
+                self._flags = PeerBuffers(256, group)
+                check(lib().genfft_cuda_memset_dev(self._flags.local, 0, 256))
+                self._flag_ptrs = (C.c_void_p * self.world)(*self._flags.ptrs)
+                self._epoch = 0
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+
+    _stream_barrier = DistFFT2D._stream_barrier
+
+    def transform(self, shard, inv: bool = False):
+        """`shard`: this rank's n/P contiguous input points.  Returns this rank's n/P natural-order output points, or
+        with ``transposed_out`` its (H/P x W) slab Z[kr][kc] = X[kr + H*kc]."""
+        e = self.engine
+        if shard.numel() != self.hl * self.w:
+            raise ValueError(f"expected this rank's {self.hl * self.w} contiguous points")
+        x = shard.reshape(self.hl, self.w)
+        row0 = self.rank * self.hl
+        if self.transport == "nccl":
+            e.pack_cols(self.send, x)
+            dist.all_to_all_single(self.block.view(self.world, self.hl, self.wp), self.send, group=self.group)
+            e.cols(self.block_out, self.block, inv)
+            dist.all_to_all_single(self.recv2, self.block_out.view(self.world, self.hl, self.wp), group=self.group)
+            e.unpack(self.slab, self.recv2)
+            e.twiddle(self.slab, row0, inv)
+            if self.transposed_out:
+                e.rows(self.out, self.slab, inv)
+                return self.out
+            e.rows_pack(self.slab, self.send, inv)
+            dist.all_to_all_single(self.block.view(self.world, self.hl, self.wp), self.send, group=self.group)
+            e.transpose(self.out, self.block)
+            return self.out.view(-1)
+        self._stream_barrier()  # peers are done with the block / slab buffers of the previous call
+        e.cols_blocks_to_peers(x, self.block_buf.ptrs, self.rank)                    # transpose 1
+        self._stream_barrier()
+        e.cols_to_peers(self.block_buf.local, self.slab_buf.ptrs, self.rank, inv)    # column transforms + transpose 2
+        self._stream_barrier()
+        e.twiddle(self.slab, row0, inv)
+        if self.transposed_out:
+            e.rows(self.out, self.slab, inv)
+            return self.out
+        e.rows_to_peers(self.slab, self.block_buf.ptrs, self.rank, inv)              # row transforms + transpose 3
+        self._stream_barrier()
+        e.transpose(self.out, self.block)
+        return self.out.view(-1)
+
+    def close(self):
+        if self.transport == "p2p":
+            if getattr(self, "_flags", None) is not None:
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+                self._flags.close()
+                self._flags = None
+            self.block_buf.close()
+            self.slab_buf.close()

@@ -181,6 +181,17 @@ int genfft_cuda_copy2d_dev(int precision, void* out, int64_t out_stride, int64_t
                            int64_t in_stride, int64_t in_dist, int64_t rows, int64_t cols, int64_t batch,
                            void* stream);
 
+/* ---- distributed four-step 1D building blocks (genfft_b200/dist.py::DistFFT1D) ---------------------------------
+ * A transform of N = H*W points, seen as an H x W row-major matrix whose row slabs live on different GPUs, is
+ * column transforms (dist_cols above), the twiddle W_N^(kr*c), and row transforms (dist_rows above); nothing in the
+ * reference corresponds to it (genFFT is single-threaded, one address space).
+ * twiddle2d: data[r*stride + c] *= W_N^((row0 + r) * c) in place (conjugated for the inverse), N = n_total.
+ * transpose: out[c*out_stride + r] = in[r*in_stride + c] (natural-order output of the four-step transform). */
+int genfft_cuda_twiddle2d_dev(int precision, void* data, int64_t stride, int64_t rows, int64_t cols, int64_t row0,
+                              int64_t n_total, int inverse, void* stream);
+int genfft_cuda_transpose_dev(int precision, void* out, int64_t out_stride, const void* in, int64_t in_stride,
+                              int64_t rows, int64_t cols, void* stream);
+
 /* Test hook: x / d as the kernels compute it when they decode a tile index (magic-number multiply, exact for
  * x < 2^31); host code only. */
 uint32_t genfft_cuda_debug_fast_div(uint32_t x, uint32_t d);

@@ -9,7 +9,46 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from genfft_b200.dist import DistFFT2D  # noqa: E402
+from genfft_b200.dist import DistFFT1D, DistFFT2D, four_step_shape  # noqa: E402
+
+
+def one_d_cases(rank, world):
+    """Distributed four-step 1D transform against numpy's fft of the whole sequence."""
+    fails = 0
+    for lg, dt in ((6, np.float32), (12, np.float32), (20, np.float32), (22, np.float32), (16, np.float64), (21, np.float64)):
+        n = 1 << lg
+        try:
+            h, w = four_step_shape(n, world)
+        except ValueError:
+            continue
+        cd = np.complex64 if dt == np.float32 else np.complex128
+        rng = np.random.default_rng(lg)
+        full = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(cd)
+        want_f = np.fft.fft(full.astype(np.complex128))
+        want_i = np.fft.ifft(full.astype(np.complex128)) * n
+        tol = (1e-6 if dt == np.float32 else 1e-14) * lg
+        shard = torch.from_numpy(full[rank * n // world:(rank + 1) * n // world].copy()).cuda()
+        for transport, bar in (("nccl", "collective"), ("p2p", "flags"), ("p2p", "collective")):
+            for transposed in (False, True):
+                plan = DistFFT1D(n, dt, transport=transport, transposed_out=transposed, barrier=bar)
+                for inv, want in ((False, want_f), (True, want_i)):
+                    for rep in range(2):  # twice: buffers are reused between calls
+                        got = plan.transform(shard, inv)
+                        torch.cuda.synchronize()
+                    got = got.cpu().numpy()
+                    if transposed:  # Z[kr][kc] = X[kr + H*kc], this rank's rows kr
+                        ref = want.reshape(w, h).T[rank * h // world:(rank + 1) * h // world]
+                    else:
+                        ref = want[rank * n // world:(rank + 1) * n // world]
+                    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+                    ok = err <= tol
+                    fails += not ok
+                    if rank == 0 or not ok:
+                        print(f"[rank {rank}] 1D n=2^{lg} {dt.__name__} {transport}/{bar} transposed={transposed} inv={inv}: "
+                              f"rel-L2 {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+                dist.barrier()
+                plan.close()
+    return fails
 
 
 def main():
@@ -52,6 +91,7 @@ def main():
                               f"rel-L2 {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
                 dist.barrier()
                 plan.close()
+    fails += one_d_cases(rank, world)
     t = torch.tensor([fails], device="cuda")
     dist.all_reduce(t)
     if rank == 0:

@@ -53,6 +53,23 @@ class CpuEngine:
     def unpack(self, out, recv):
         out.copy_(recv.permute(1, 0, 2).reshape(self.hl, self.w))
 
+    # the extra local steps of the distributed four-step 1D transform
+    def pack_cols(self, send, slab):
+        send.copy_(slab.reshape(self.hl, self.p, self.wp).permute(1, 0, 2))
+
+    def twiddle(self, slab, row0, inv):
+        kr = np.arange(row0, row0 + self.hl)[:, None]
+        c = np.arange(self.w)[None, :]
+        tw = np.exp((2j if inv else -2j) * np.pi * (kr * c) / (self.w * self.h))
+        slab.copy_(torch.from_numpy(slab.numpy() * tw))
+
+    def rows(self, out, slab, inv):
+        x = slab.numpy()
+        out.copy_(torch.from_numpy(np.fft.ifft(x, axis=1) * self.w if inv else np.fft.fft(x, axis=1)))
+
+    def transpose(self, out, block):
+        out.copy_(block.t())
+
 
 def _worker(rank, world, port, w, h, transposed, inv, q):
     sys.path.insert(0, ROOT)
@@ -96,3 +113,56 @@ def test_slab_2d_orchestration_gloo(world, transposed, inv):
         assert p.exitcode == 0
     errs = dict(q.get(timeout=10) for _ in range(world))
     assert len(errs) == world and max(errs.values()) < 1e-12, errs
+
+
+def _worker_1d(rank, world, port, n, transposed, inv, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from genfft_b200.dist import DistFFT1D, four_step_shape
+        rng = np.random.default_rng(11)
+        full = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+        h, w = four_step_shape(n, world)
+        plan = DistFFT1D(n, np.float64, transport="nccl", transposed_out=transposed, engine=CpuEngine(w, h, world))
+        shard = torch.from_numpy(full[rank * n // world:(rank + 1) * n // world].copy())
+        got = plan.transform(shard, inv).numpy()
+        want = np.fft.ifft(full) * n if inv else np.fft.fft(full)
+        if transposed:  # Z[kr][kc] = X[kr + H*kc], this rank's rows kr
+            want = want.reshape(w, h).T[rank * h // world:(rank + 1) * h // world]
+        else:
+            want = want[rank * n // world:(rank + 1) * n // world]
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        q.put((rank, float(err)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 64), (4, 512)])
+@pytest.mark.parametrize("transposed,inv", [(False, False), (True, False), (False, True)])
+def test_four_step_1d_orchestration_gloo(world, n, transposed, inv):
+    """DistFFT1D: the three global transposes, the twiddle's row offset and the output order, against numpy's fft of
+    the whole sequence (local steps by the numpy test double)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_1d, args=(r, world, port, n, transposed, inv, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    errs = dict(q.get(timeout=10) for _ in range(world))
+    assert len(errs) == world and max(errs.values()) < 1e-12, errs
+
+
+def test_four_step_shape():
+    from genfft_b200.dist import four_step_shape
+    assert four_step_shape(1 << 24, 8) == (4096, 4096)
+    assert four_step_shape(1 << 25, 8) == (4096, 8192)
+    assert four_step_shape(64, 2) == (8, 8)
+    with pytest.raises(ValueError):
+        four_step_shape(16, 8)  # H = 4 rows cannot be split over 8 ranks
+    with pytest.raises(ValueError):
+        four_step_shape(48, 2)

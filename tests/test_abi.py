@@ -121,3 +121,22 @@ def test_tile_decode_division_is_exact():
         for x in xs:
             if 0 <= x <= top:
                 assert f(x, d) == x // d, (x, d)
+
+
+def test_bench_reference_arm_prints_one_json_line(checkers):
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) needs no GPU: exactly one line on stdout,
+    the contract keys, and an e2e entry without host<->device bytes."""
+    import json
+    import sys
+    if checkers[0] is None:
+        pytest.skip("compiled reference not present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[-1000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GFLOP/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["vs_baseline"] is None

@@ -163,6 +163,30 @@ class _Lib:
         return o1, o2
 
 
+    # --- RealFFT2D<T> (FFTReal.h:71-184) ---
+    def real_fft2d(self, x: np.ndarray) -> np.ndarray:
+        """RealFFT2D<T>::forward (FFTReal.h:83-104); x is (height, width) real."""
+        x = np.ascontiguousarray(x)
+        h, w = x.shape
+        out = np.zeros((h, w), dtype=_CPX[x.dtype])
+        f = self._fn("real_fft2d", x.dtype,
+                     argtypes=[_c.c_void_p, _c.c_long, _c.c_void_p, _c.c_long, _c.c_int, _c.c_int])
+        if f(_ptr(out), w, _ptr(x), w, w, h):
+            raise ValueError("real_fft2d rejected size")
+        return out
+
+    def real_fft2d_2x(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """RealFFT2D<T>::forward_2x (FFTReal.h:114-118) with equal input strides; a, b are (height, width) real."""
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        h, w = a.shape
+        out = np.zeros((h, w), dtype=_CPX[a.dtype])
+        f = self._fn("real_fft2d_2x", a.dtype,
+                     argtypes=[_c.c_void_p, _c.c_long, _c.c_void_p, _c.c_void_p, _c.c_long, _c.c_int, _c.c_int])
+        if f(_ptr(out), w, _ptr(a), _ptr(b), w, w, h):
+            raise ValueError("real_fft2d_2x rejected size")
+        return out
+
+
 class Port(_Lib):
     """The plain-C restatement (genfft_oracle.c)."""
     prefix = "oracle_"
@@ -222,28 +246,6 @@ class Ref(_Lib):
         f.restype = _c.c_int
         f.argtypes = [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int]
         f(_ptr(out), _ptr(x), x.shape[-1], int(inverse))
-        return out
-
-    def real_fft2d(self, x: np.ndarray) -> np.ndarray:
-        """RealFFT2D<T>::forward (FFTReal.h:83-104); x is (height, width) real."""
-        x = np.ascontiguousarray(x)
-        h, w = x.shape
-        out = np.zeros((h, w), dtype=_CPX[x.dtype])
-        f = self._fn("real_fft2d", x.dtype,
-                     argtypes=[_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int])
-        if f(_ptr(out), w, _ptr(x), w, w, h):
-            raise ValueError("real_fft2d rejected size")
-        return out
-
-    def real_fft2d_2x(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
-        """RealFFT2D<T>::forward_2x (FFTReal.h:114-118) with equal input strides; a, b are (height, width) real."""
-        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
-        h, w = a.shape
-        out = np.zeros((h, w), dtype=_CPX[a.dtype])
-        f = self._fn("real_fft2d_2x", a.dtype,
-                     argtypes=[_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int])
-        if f(_ptr(out), w, _ptr(a), _ptr(b), w, w, h):
-            raise ValueError("real_fft2d_2x rejected size")
         return out
 
     # ---- CPU-baseline timing (restated test/fft_bench.cpp loops; seconds inside transform calls) ----

@@ -2,9 +2,9 @@
  *
  * Plain-C CPU restatement of the algorithm of mzient/genFFT (the reference) for the
  * transform hot path: bit-reversal scramble + in-place radix-2 decimation-in-time levels with
- * per-level fp64-computed twiddle tables, the real-FFT split ("DIT"), the vertical (column) FFT
- * and the 2D transform.  Every function cites the reference file:line it follows (see
- * genfft_oracle_impl.inc).
+ * per-level fp64-computed twiddle tables, the real-FFT split ("DIT"), the vertical (column) FFT,
+ * the 2D transform and the real-image 2D transforms (RealFFT2D forward / forward_2x).  Every
+ * function cites the reference file:line it follows (see genfft_oracle_impl.inc).
  *
  * Parity status: PINNED.  tests/test_oracle.py checks this restatement
  *   (1) bit for bit against the reference's own generic scalar back-end compiled from

@@ -214,17 +214,17 @@ int genfft_ref_fft2d_f32(float *out, long os, const float *in, long is, int w, i
 int genfft_ref_fft2d_f64(double *out, long os, const double *in, long is, int w, int h, int inv) {
   return fft2d<double>(out, os, in, is, w, h, inv);
 }
-int genfft_ref_real_fft2d_f32(float *out, int os, const float *in, int is, int w, int h) {
-  return real_fft2d<float>(out, os, in, is, w, h);
+int genfft_ref_real_fft2d_f32(float *out, long os, const float *in, long is, int w, int h) {
+  return real_fft2d<float>(out, (int)os, in, (int)is, w, h);
 }
-int genfft_ref_real_fft2d_f64(double *out, int os, const double *in, int is, int w, int h) {
-  return real_fft2d<double>(out, os, in, is, w, h);
+int genfft_ref_real_fft2d_f64(double *out, long os, const double *in, long is, int w, int h) {
+  return real_fft2d<double>(out, (int)os, in, (int)is, w, h);
 }
-int genfft_ref_real_fft2d_2x_f32(float *out, int os, const float *in1, const float *in2, int is, int w, int h) {
-  return real_fft2d_2x<float>(out, os, in1, in2, is, w, h);
+int genfft_ref_real_fft2d_2x_f32(float *out, long os, const float *in1, const float *in2, long is, int w, int h) {
+  return real_fft2d_2x<float>(out, (int)os, in1, in2, (int)is, w, h);
 }
-int genfft_ref_real_fft2d_2x_f64(double *out, int os, const double *in1, const double *in2, int is, int w, int h) {
-  return real_fft2d_2x<double>(out, os, in1, in2, is, w, h);
+int genfft_ref_real_fft2d_2x_f64(double *out, long os, const double *in1, const double *in2, long is, int w, int h) {
+  return real_fft2d_2x<double>(out, (int)os, in1, in2, (int)is, w, h);
 }
 // FFT::transform_real / transform_interleave + separate_2x_real_FFT (fft.h:90-105, FFTReal.h:35-66)
 int genfft_ref_transform_real_f32(float *out, const float *in, int n) {

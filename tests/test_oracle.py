@@ -192,17 +192,26 @@ def test_reference_2pow24_hook(ref):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-def test_reference_real_fft2d_matches_numpy(checkers, dt):
-    """RealFFT2D::forward and forward_2x (FFTReal.h:83-118) have no test in the reference: pin the compiled
-    reference's outputs (the comparands of the GPU parity tests) against numpy's fft2."""
-    ref = checkers[0]
-    if ref is None:
-        pytest.skip("compiled reference not present")
-    for w, h in [(4, 2), (8, 8), (64, 16), (16, 128), (512, 32)]:
+def test_real_fft2d_restatement_and_reference_match_numpy(checkers, dt):
+    """RealFFT2D::forward and forward_2x (FFTReal.h:83-118) have no test in the reference: pin the restatement and,
+    where present, the compiled reference (the comparands of the GPU parity tests) against numpy's fft2 and against
+    each other (the reference's RealFFT2D has no factory parameter, so it always runs the dispatch back-end: equal
+    within rounding, identical where no twiddle is involved)."""
+    ref, port = checkers
+    for w, h in [(1, 1), (2, 1), (2, 2), (4, 2), (8, 8), (64, 16), (16, 128), (512, 32)]:
         rng = np.random.default_rng(w * 31 + h)
         a = rng.uniform(-1, 1, (h, w)).astype(dt)
         b = rng.uniform(-1, 1, (h, w)).astype(dt)
-        tol = oracle.tolerance(w * h, dt)
-        assert oracle.rel_l2(ref.real_fft2d(a), np.fft.fft2(a.astype(np.float64))) <= tol
-        want = np.fft.fft2(a.astype(np.float64) + 1j * b.astype(np.float64))
-        assert oracle.rel_l2(ref.real_fft2d_2x(a, b), want) <= tol
+        tol = oracle.tolerance(w * h, dt) / 10
+        want = np.fft.fft2(a.astype(np.float64))
+        want2 = np.fft.fft2(a.astype(np.float64) + 1j * b.astype(np.float64))
+        for impl in (port, ref):
+            if impl is None:
+                continue
+            assert oracle.rel_l2(impl.real_fft2d(a), want) <= tol, (w, h)
+            assert oracle.rel_l2(impl.real_fft2d_2x(a, b), want2) <= tol, (w, h)
+        if ref is not None:
+            assert oracle.rel_l2(port.real_fft2d(a), ref.real_fft2d(a)) <= tol
+            assert oracle.rel_l2(port.real_fft2d_2x(a, b), ref.real_fft2d_2x(a, b)) <= tol
+            if w * h <= 8:  # butterflies without multiplications: the two agree bit for bit
+                assert np.array_equal(bits(port.real_fft2d(a)), bits(ref.real_fft2d(a)))

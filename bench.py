@@ -317,11 +317,37 @@ def main() -> int:
                                     "sample": f"unavailable: {e}"}
         if not args.no_extras:
             line["extras"] = extras(g, np, torch)
+            try:
+                line["extras"]["cpu_reference_1_thread"] = cpu_reference_extras(np)
+            except Exception as e:  # reported beside the GPU numbers; never in their way
+                line["extras"]["cpu_reference_1_thread"] = {"error": repr(e)}
     print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def cpu_reference_extras(np) -> dict:
+    """genFFT's own CPU implementation (oracle/_ref, one thread -- the library is single-threaded) on the secondary
+    configs, timed like test/fft_bench.cpp (std::chrono around the transform calls, fresh input per call): C1 exactly,
+    C3 through the factory hook that lifts the reference past its 2^23 size switch, C4 on two of its 256 transforms,
+    C5 on an 8192^2 image scaled by the 5 N log2 N work ratio."""
+    import oracle
+    ref = oracle.Ref()
+    out = {}
+    t = ref.bench_c2c(1024, 20000, 1, np.float32, fwd_only=False) / 20000
+    out["C1_1d_c2c_f32_n1024_fwd_inv"] = {"us_per_pair": t * 1e6, "gflops": 2 * 5 * 1024 * 10 / t / 1e9}
+    t = ref.bench_c2c(1 << 24, 1, 1, np.float64)
+    out["C3_1d_c2c_f64_n2^24"] = {"ms": t * 1e3, "gflops": 5 * (1 << 24) * 24 / t / 1e9}
+    t = ref.bench_r2c(1 << 22, 2, 1) / 2
+    out["C4_1d_r2c_f32_n2^22_x256"] = {"ms_per_transform": t * 1e3, "ms_batch_of_256_extrapolated": t * 256 * 1e3,
+                                       "gflops_2.5NlogN": 2.5 * (1 << 22) * 22 / t / 1e9}
+    t = ref.bench_fft2d(8192, 8192, 1)
+    scale = (32768.0 ** 2 * 30) / (8192.0 ** 2 * 26)
+    out["C5_2d_c2c_f32_32768^2"] = {"ms_8192^2_measured": t * 1e3, "ms_32768^2_extrapolated": t * scale * 1e3,
+                                    "gflops_at_8192^2": 5 * 8192.0 ** 2 * 26 / t / 1e9}
+    return out
 
 
 def extras(g, np, torch) -> dict:

@@ -1,0 +1,12 @@
+#!/bin/bash
+# First GPU call of a round (1 GPU): state of the tree on real hardware in one go.
+#   gpurun --timeout 600 -- bash tools/round_start.sh
+# Writes everything under gpurun_out/ (merged back by gpurun).
+set -u
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+(time python -m pytest tests -m gpu -q --durations=10 --maxfail=10) > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+(time python bench.py) > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -c 300 gpurun_out/bench_1gpu.json; echo
+python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_reference.json 2>/dev/null
+python tools/quick_bench.py c3 c4 2d > gpurun_out/quick_bench.log 2>&1; cut -c1-100 gpurun_out/quick_bench.log
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a tools/tma_tile_bench.cu -o /tmp/tma_tile_bench && timeout 30 /tmp/tma_tile_bench > gpurun_out/tma_tile_bench.log 2>&1

@@ -22,6 +22,7 @@ SIZES_1D = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 4096]
 SIZES_R2C = [1, 2, 4, 8, 16, 64, 256, 1024, 4096]
 VERT = [(2, 3), (4, 7), (8, 33), (64, 5), (256, 9)]
 TWO_D = [(4, 8), (64, 32), (128, 16)]  # (width, height)
+REAL_2D = [(2, 2), (4, 2), (8, 8), (64, 32), (128, 16), (16, 64)]  # (width, height)
 
 
 def main():
@@ -55,6 +56,19 @@ def main():
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "genfft_golden.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; {ref.describe()}")
+    # RealFFT2D::forward / forward_2x (FFTReal.h:83-118), added later: a second file so that the first stays as it was
+    out = {}
+    for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
+        for w, h in REAL_2D:
+            ab = ref.dummy_real(2 * w * h, dt)
+            a, b = ab[: w * h].reshape(h, w), ab[w * h:].reshape(h, w)
+            out[f"real2d_{tag}_{w}x{h}_in1"] = a
+            out[f"real2d_{tag}_{w}x{h}_in2"] = b
+            out[f"real2d_{tag}_{w}x{h}_forward"] = ref.real_fft2d(a)
+            out[f"real2d_{tag}_{w}x{h}_forward_2x"] = ref.real_fft2d_2x(a, b)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "genfft_golden_real2d.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":

@@ -310,6 +310,23 @@ def test_real_fft2d_forward_2x(checkers, monkeypatch, fused, dt, w, h):
     assert oracle.rel_l2(h_out, got) <= 1e-6
 
 
+@pytest.mark.parametrize("tag,dt", [("f32", np.float32), ("f64", np.float64)])
+def test_real_fft2d_vs_committed_reference_outputs(tag, dt):
+    """RealFFT2D::forward / forward_2x against tests/golden/genfft_golden_real2d.npz (outputs of the reference itself,
+    generated by tests/golden/make_golden.py): the pin that needs neither /root/reference nor its prebuilt library."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "genfft_golden_real2d.npz"))
+    for key in [k for k in gold.files if k.startswith(f"real2d_{tag}_") and k.endswith("_in1")]:
+        w, h = (int(v) for v in key.split("_")[2].split("x"))
+        a, b = gold[key], gold[key.replace("_in1", "_in2")]
+        plan = g.RealFFT2D(w, h, dt)
+        out = torch.empty((h, w), dtype=TCPX[dt], device="cuda")
+        plan.forward(out, torch.from_numpy(a).cuda())
+        assert oracle.rel_l2(out.cpu().numpy(), gold[key.replace("_in1", "_forward")]) <= oracle.tolerance(w * h, dt), key
+        plan.forward_2x(out, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+        assert oracle.rel_l2(out.cpu().numpy(), gold[key.replace("_in1", "_forward_2x")]) <= oracle.tolerance(w * h, dt), key
+
+
 def test_real_fft2d_forward_2x_errors():
     plan = g.RealFFT2D(8, 4, np.float32)
     a = torch.zeros((4, 8), device="cuda")

@@ -215,3 +215,19 @@ def test_real_fft2d_restatement_and_reference_match_numpy(checkers, dt):
             assert oracle.rel_l2(port.real_fft2d_2x(a, b), ref.real_fft2d_2x(a, b)) <= tol
             if w * h <= 8:  # butterflies without multiplications: the two agree bit for bit
                 assert np.array_equal(bits(port.real_fft2d(a)), bits(ref.real_fft2d(a)))
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_port_real_fft2d_vs_reference_fixtures(port, tag):
+    """The restatement of RealFFT2D::forward / forward_2x against the committed outputs of the reference (dispatch
+    back-end -- RealFFT2D has no factory parameter, so no generic-back-end output exists to be bit-exact with)."""
+    gold2 = np.load(os.path.join(os.path.dirname(GOLD), "genfft_golden_real2d.npz"))
+    keys = [k for k in gold2.files if k.startswith(f"real2d_{tag}_") and k.endswith("_in1")]
+    assert len(keys) == 6
+    for key in keys:
+        w, h = (int(v) for v in key.split("_")[2].split("x"))
+        a, b = gold2[key], gold2[key.replace("_in1", "_in2")]
+        tol = oracle.tolerance(w * h, DT[tag]) / 10
+        assert oracle.rel_l2(port.real_fft2d(a), gold2[key.replace("_in1", "_forward")]) <= tol, key
+        assert oracle.rel_l2(port.real_fft2d_2x(a, b), gold2[key.replace("_in1", "_forward_2x")]) <= tol, key
+        assert oracle.rel_l2(gold2[key.replace("_in1", "_forward")], np.fft.fft2(a.astype(np.float64))) <= tol

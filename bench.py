@@ -85,7 +85,7 @@ class ClockSampler:
                             rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                         except Exception:
                             rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                        self.samples.append((int(clk), int(rs)))
+                        self.samples.append((time.perf_counter(), int(clk), int(rs)))
                     except Exception as e:  # keep the bench alive
                         self.err = repr(e)
                         return
@@ -96,20 +96,26 @@ class ClockSampler:
         except Exception as e:
             self.err = repr(e)
 
-    def stop(self) -> dict:
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """Median SM clock and throttle reasons of the samples taken inside the host-time window [t0, t1] (the timed
+        region; the thread is started before the warm-up so that NVML's first-call latency is not inside it)."""
         self.stop_flag.set()
         if self.thread is not None:
             self.thread.join(timeout=1.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": [f"unavailable: {self.err}"]}
-        clocks = sorted(c for c, _ in self.samples)
+        inside = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)]
+        if not inside:  # region shorter than one NVML round trip: the sample closest to it
+            mid = 0.5 * ((t0 or 0.0) + (t1 or 0.0))
+            inside = [min(self.samples, key=lambda s: abs(s[0] - mid))]
+        clocks = sorted(c for _, c, _ in inside)
         seen = set()
-        for _, rs in self.samples:
+        for _, _, rs in inside:
             for bit, name in self.REASONS.items():
                 if rs & bit:
                     seen.add(name)
         return {"sm_mhz": float(clocks[len(clocks) // 2]), "sm_max_mhz": self.max_mhz, "samples": len(clocks),
-                "reasons": sorted(seen)}
+                "samples_total": len(self.samples), "reasons": sorted(seen)}
 
 
 def claim_stdout():
@@ -207,22 +213,24 @@ def main() -> int:
     x = torch.view_as_complex(torch.rand((BATCH, N_FFT, 2), generator=gen, device="cuda") * 2 - 1)
     y = torch.empty_like(x)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: NVML's first calls are slow and must not eat the timed region
     for _ in range(args.warmup):
         plan.forward(y, x)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = g.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    t_host0 = time.perf_counter()
     ev[0].record()
     for i in range(args.steps):
         plan.forward(y, x)
         ev[i + 1].record()
     barrier()
+    t_host1 = time.perf_counter()
     launches = g.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     per_kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     if world > 1:

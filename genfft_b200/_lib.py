@@ -106,6 +106,10 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(genfft_b200 has no CPU or PyTorch fallback)")
         handle = C.CDLL(LIB_PATH)
+        if hasattr(handle, "genfft_emu_fiber_switches"):
+            # tests/emu builds the kernel sources for host fibers to test their logic without a GPU; it is not a backend
+            raise GenfftCudaError(f"{LIB_PATH} is the test suite's kernel-logic emulator, not libgenfft_cuda "
+                                  "(genfft_b200 has no CPU or PyTorch fallback)")
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = res

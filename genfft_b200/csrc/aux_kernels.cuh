@@ -308,6 +308,7 @@ struct PeerBarrierParams {
   uint32_t epoch;  // strictly increasing per barrier
 };
 
+#ifndef GENFFT_EMU
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerBarrierParams p) {
   const int r = threadIdx.x;
   if (r >= p.world) return;
@@ -322,5 +323,12 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
     if (++spins > (1u << 27)) __trap();  // ~15 s: a peer that never arrives must fail loudly, never hang the GPU
   }
 }
+#else
+// emulator: ranks run one after another in one process, so the barrier only publishes the arrival
+inline void peer_barrier_kernel(const PeerBarrierParams p) {
+  const int r = threadIdx.x;
+  if (r < p.world) p.peer_flags[r][p.rank] = p.epoch;
+}
+#endif
 
 }  // namespace genfft_cuda

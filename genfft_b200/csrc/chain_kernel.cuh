@@ -31,6 +31,7 @@ struct ChainParams {
   uint32_t* ctr;    // [0]: ticket, [1 + g]: finished A tiles of group g; zeroed before the launch
 };
 
+#ifndef GENFFT_EMU  // emu_device.h restates these for the CPU tests
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -44,6 +45,7 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+#endif
 
 template <typename T, int THREADS>
 constexpr int chain_min_blocks() {
@@ -57,7 +59,7 @@ template <typename T, class KA, class KB>
 __global__ void __launch_bounds__(KA::THREADS, chain_min_blocks<T, KA::THREADS>())
 fft_chain_kernel(const __grid_constant__ ChainParams cp) {
   static_assert(KA::THREADS == KB::THREADS, "chained passes must have the same CTA size");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GENFFT_DYN_SMEM(smem_raw);
   __shared__ uint32_t s_ticket[2];
   const uint32_t ta = cp.ta, tb = cp.tb, ng = cp.ngroups, lag = cp.lag;
   const uint32_t per = ta + tb;

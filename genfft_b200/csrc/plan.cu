@@ -21,6 +21,7 @@
 
 #include "../../include/genfft_cuda.h"
 #include "aux_kernels.cuh"
+#include "launch.h"
 #include "plan.h"
 
 namespace genfft_cuda {
@@ -629,7 +630,7 @@ static int launch_copy_t(const CopyParams& cp, long long batch, cudaStream_t str
   if (cp.rows <= 0 || cp.cols <= 0 || batch <= 0) return GENFFT_CUDA_OK;
   dim3 grid((unsigned)std::min<long long>((cp.cols + 255) / 256, 65535), (unsigned)std::min<long long>(cp.rows, 65535),
             (unsigned)batch);
-  copy_kernel<T><<<grid, 256, 0, stream>>>(cp);
+  GENFFT_LAUNCH((copy_kernel<T>), grid, 256, 0, stream, cp);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
@@ -656,9 +657,9 @@ static int launch_dit(const Plan* plan, void* out, long long out_dist, const voi
   const int work = n / 4 + 1;
   dim3 grid((unsigned)std::min((work + 255) / 256, 4096), (unsigned)std::min<long long>(batch, 65535));
   if (plan->precision == GENFFT_CUDA_F32)
-    dit_kernel<float><<<grid, 256, 0, stream>>>(d);
+    GENFFT_LAUNCH((dit_kernel<float>), grid, 256, 0, stream, d);
   else
-    dit_kernel<double><<<grid, 256, 0, stream>>>(d);
+    GENFFT_LAUNCH((dit_kernel<double>), grid, 256, 0, stream, d);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
@@ -1338,9 +1339,9 @@ int genfft_cuda_separate_2x_real_dev(int precision, void* out1, void* out2, cons
   sp.n = (int)n;
   const unsigned grid = (unsigned)std::min<long long>((n / 2 + 1 + 255) / 256, 8192);
   if (precision == GENFFT_CUDA_F32)
-    separate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(sp);
+    GENFFT_LAUNCH((separate_kernel<float>), grid, 256, 0, (cudaStream_t)stream, sp);
   else
-    separate_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(sp);
+    GENFFT_LAUNCH((separate_kernel<double>), grid, 256, 0, (cudaStream_t)stream, sp);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
@@ -1415,9 +1416,9 @@ int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_
     mp.h = (int)p->height;
     dim3 grid((unsigned)std::min<long long>((p->width / 2 + 255) / 256, 1024), (unsigned)std::min<long long>(p->height, 65535));
     if (p->precision == GENFFT_CUDA_F32)
-      mirror2d_kernel<float><<<grid, 256, 0, st>>>(mp);
+      GENFFT_LAUNCH((mirror2d_kernel<float>), grid, 256, 0, st, mp);
     else
-      mirror2d_kernel<double><<<grid, 256, 0, st>>>(mp);
+      GENFFT_LAUNCH((mirror2d_kernel<double>), grid, 256, 0, st, mp);
     g_launches++;
     CU_TRY(cudaGetLastError());
   }
@@ -1525,9 +1526,9 @@ int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in,
   cp.tw_shift = p->dit_shift;
   dim3 grid((unsigned)std::min<long long>((M + 255) / 256, 4096), (unsigned)std::min<long long>(p->batch, 65535));
   if (p->precision == GENFFT_CUDA_F32)
-    c2r_pre_kernel<float><<<grid, 256, 0, st>>>(cp);
+    GENFFT_LAUNCH((c2r_pre_kernel<float>), grid, 256, 0, st, cp);
   else
-    c2r_pre_kernel<double><<<grid, 256, 0, st>>>(cp);
+    GENFFT_LAUNCH((c2r_pre_kernel<double>), grid, 256, 0, st, cp);
   g_launches++;
   CU_TRY(cudaGetLastError());
   if (p->seq.passes.empty()) {  // M == 1: the inverse transform is the identity
@@ -1763,9 +1764,9 @@ int genfft_cuda_twiddle2d_dev(int precision, void* data, int64_t stride, int64_t
   tp.inverse = inverse ? 1 : 0;
   dim3 grid((unsigned)std::min<long long>((cols + 255) / 256, 1024), (unsigned)std::min<long long>(rows, 65535));
   if (precision == GENFFT_CUDA_F32)
-    twiddle2d_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+    GENFFT_LAUNCH((twiddle2d_kernel<float>), grid, 256, 0, (cudaStream_t)stream, tp);
   else
-    twiddle2d_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+    GENFFT_LAUNCH((twiddle2d_kernel<double>), grid, 256, 0, (cudaStream_t)stream, tp);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
@@ -1788,9 +1789,9 @@ int genfft_cuda_transpose_dev(int precision, void* out, int64_t out_stride, cons
   const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
   const unsigned grid = (unsigned)std::min<long long>(tiles, 1LL << 20);
   if (precision == GENFFT_CUDA_F32)
-    transpose_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+    GENFFT_LAUNCH((transpose_kernel<float>), grid, 256, 0, (cudaStream_t)stream, tp);
   else
-    transpose_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(tp);
+    GENFFT_LAUNCH((transpose_kernel<double>), grid, 256, 0, (cudaStream_t)stream, tp);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
@@ -1810,7 +1811,7 @@ int genfft_cuda_peer_barrier_dev(void* const* peer_flags, int rank, int world, u
   p.rank = rank;
   p.world = world;
   p.epoch = epoch;
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+  GENFFT_LAUNCH((peer_barrier_kernel), 1, 32, 0, (cudaStream_t)stream, p);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <vector>
+#include "launch.h"
 #include "tile_kernel.cuh"
 #include "chain_kernel.cuh"
 
@@ -23,7 +24,7 @@ struct KernelEntry {
 template <typename T, int L, int P, int C, int MODE, bool INV>
 void launch_tile(const PassParams& prm, int grid, cudaStream_t stream) {
   using K = TileKernel<T, L, P, C, MODE, INV>;
-  fft_tile_kernel<T, L, P, C, MODE, INV><<<grid, K::THREADS, K::SMEM_BYTES, stream>>>(prm);
+  GENFFT_LAUNCH((fft_tile_kernel<T, L, P, C, MODE, INV>), grid, K::THREADS, K::SMEM_BYTES, stream, prm);
 }
 
 template <typename T, int L, int P, int C, int MODE>
@@ -84,7 +85,7 @@ struct ChainEntry {
 template <typename T, class KA, class KB>
 void launch_chain_t(const ChainParams& cp, unsigned grid, cudaStream_t stream) {
   constexpr size_t smem = KA::SMEM_BYTES > KB::SMEM_BYTES ? KA::SMEM_BYTES : KB::SMEM_BYTES;
-  fft_chain_kernel<T, KA, KB><<<grid, KA::THREADS, smem, stream>>>(cp);
+  GENFFT_LAUNCH((fft_chain_kernel<T, KA, KB>), grid, KA::THREADS, smem, stream, cp);
 }
 
 // INV applies to the compile-time-direction modes; M_GEN takes the direction from PassParams::inverse

@@ -17,6 +17,7 @@
 #pragma once
 #include <cstdint>
 #include <type_traits>
+#include "launch.h"
 #include "radix.cuh"
 
 namespace genfft_cuda {
@@ -149,6 +150,9 @@ __host__ __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t mul, 
 #endif
 }
 
+#ifdef GENFFT_EMU
+#include "emu_device.h"  // tests/emu: host restatement of the PTX helpers below (CPU tests only)
+#else
 // ---- mbarrier / bulk-copy PTX (sm_90+; SASS: SYNCS / UBLKCP) ---------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -178,6 +182,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+#endif  // GENFFT_EMU
 
 // Cache operators of the data loads/stores.  The stand-alone kernels use the defaults; the L2-resident pass chains
 // (chain_kernel.cuh) stream their HBM-side traffic (evict-first) and read the intermediate, which another SM wrote
@@ -195,6 +200,7 @@ __device__ __forceinline__ void st_data(V* p, const V& v) {
   else *p = v;
 }
 
+#ifndef GENFFT_EMU
 // Strided global access  base[stride * k]  with the address formed by ONE instruction (IMAD.WIDE.U32 with an
 // immediate): `stride` is a 32-bit element stride, `k` a compile-time element count after unrolling.  Written in PTX
 // because the compiler otherwise strength-reduces the sixteen addresses of a tile column into chains of 64-bit
@@ -246,6 +252,7 @@ __device__ __forceinline__ double2 ldg_strided(const double2* base, uint32_t str
   asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(strided_addr(base, stride, k)));
   return v;
 }
+#endif  // GENFFT_EMU
 
 template <typename T, int L, int P, int C, int MODE, bool INV>
 struct TileKernel {
@@ -835,7 +842,7 @@ template <typename T, int L, int P, int C, int MODE, bool INV>
 __global__ void __launch_bounds__(TileKernel<T, L, P, C, MODE, INV>::THREADS,
                                   min_blocks<T, TileKernel<T, L, P, C, MODE, INV>::THREADS>())
 fft_tile_kernel(const __grid_constant__ PassParams prm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GENFFT_DYN_SMEM(smem_raw);
   TileKernel<T, L, P, C, MODE, INV>::body(prm, reinterpret_cast<cpx<T>*>(smem_raw));
 }
 

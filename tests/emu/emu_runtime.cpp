@@ -1,0 +1,109 @@
+// TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT (see shim/cuda_runtime.h).
+// Kernel launches of the emulated build: CTAs run one after another; the threads of a CTA are ucontext fibers that the
+// scheduler resumes in thread order, each until its next __syncthreads() (or its end).  One sweep over the live fibers
+// is one barrier phase, so code between two barriers runs thread 0, 1, 2, ... sequentially -- a read of shared memory
+// that lacks a barrier after a HIGHER-numbered thread's write sees stale data here, as it may on the device.
+#include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+
+#include <cstdio>
+#include <mutex>
+#include <vector>
+
+namespace genfft_emu {
+
+uint3 g_threadIdx, g_blockIdx;
+dim3 g_blockDim, g_gridDim;
+
+namespace {
+constexpr size_t kStackBytes = 256 * 1024;
+constexpr size_t kSmemBytes = 256 * 1024;
+
+struct Fiber {
+  ucontext_t ctx;
+  void* stack = nullptr;
+  bool done = true;
+};
+
+std::mutex g_mu;  // one launch at a time (the globals above are process-wide)
+std::vector<Fiber> g_fibers;
+ucontext_t g_main;
+const std::function<void()>* g_body = nullptr;
+Fiber* g_current = nullptr;
+alignas(128) unsigned char g_smem[kSmemBytes];
+unsigned long long g_switches = 0;
+
+void fiber_entry() {
+  (*g_body)();
+  g_current->done = true;
+  // returning resumes uc_link (the scheduler)
+}
+}  // namespace
+
+unsigned char* dyn_smem() { return g_smem; }
+
+int num_sms() {
+  const char* s = getenv("GENFFT_EMU_SMS");
+  const int v = s ? atoi(s) : 3;
+  return v > 0 ? v : 3;
+}
+
+void barrier() {
+  g_switches++;
+  swapcontext(&g_current->ctx, &g_main);
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thread_body) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const size_t nthreads = (size_t)block.x * block.y * block.z;
+  if (nthreads == 0 || nthreads > 1024 || smem > kSmemBytes) {
+    fprintf(stderr, "genfft_emu: bad launch (%zu threads, %zu bytes of shared memory)\n", nthreads, smem);
+    abort();
+  }
+  if (g_fibers.size() < nthreads) g_fibers.resize(nthreads);
+  for (size_t t = 0; t < nthreads; t++) {
+    if (!g_fibers[t].stack) {
+      void* st = mmap(nullptr, kStackBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      if (st == MAP_FAILED) abort();
+      g_fibers[t].stack = st;
+    }
+  }
+  g_body = &thread_body;
+  g_blockDim = block;
+  g_gridDim = grid;
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++) {
+        memset(g_smem, 0xEE, smem);  // shared memory is uninitialised at CTA start
+        g_blockIdx = uint3{bx, by, bz};
+        for (size_t t = 0; t < nthreads; t++) {
+          Fiber& f = g_fibers[t];
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = f.stack;
+          f.ctx.uc_stack.ss_size = kStackBytes;
+          f.ctx.uc_link = &g_main;
+          makecontext(&f.ctx, fiber_entry, 0);
+          f.done = false;
+        }
+        size_t alive = nthreads;
+        while (alive) {
+          for (size_t t = 0; t < nthreads; t++) {
+            Fiber& f = g_fibers[t];
+            if (f.done) continue;
+            const unsigned tx = (unsigned)(t % block.x), ty = (unsigned)((t / block.x) % block.y),
+                           tz = (unsigned)(t / ((size_t)block.x * block.y));
+            g_threadIdx = uint3{tx, ty, tz};
+            g_current = &f;
+            swapcontext(&g_main, &f.ctx);
+            if (f.done) alive--;
+          }
+        }
+      }
+  g_body = nullptr;
+  g_current = nullptr;
+}
+
+}  // namespace genfft_emu
+
+extern "C" unsigned long long genfft_emu_fiber_switches() { return genfft_emu::g_switches; }

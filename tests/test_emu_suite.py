@@ -1,0 +1,63 @@
+"""The -m gpu parity tests, run WITHOUT a GPU on the kernel-logic emulator (tests/emu).
+
+tests/emu compiles the real kernel and plan sources (genfft_b200/csrc/*.cu, unchanged) with g++ against a fake CUDA
+runtime: device memory is host memory, every CTA runs with its threads as fibers, __syncthreads() switches fibers.
+What this checks on a CPU-only machine is the LOGIC the GPU tests check -- tile addressing, Stockham stages, fused
+twiddles, the fused real-FFT split, pass chains and their ticket order, plan construction, the host-pointer staging
+-- against the same oracle and tolerances.  It is test infrastructure: genfft_b200 cannot load the emulator (below),
+the emulated run says nothing about performance or the inline-PTX paths, and the parity claim of the product rests on
+the -m gpu run on a real B200.
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from emu import backend  # noqa: E402
+
+GPU_TEST_FILES = ["test_gpu_c2c.py", "test_gpu_real_vert_2d.py", "test_gpu_chain.py", "test_gpu_random_sweep.py",
+                  "test_gpu_dist_kernels.py", "test_gpu_ranks_in_process.py"]
+
+
+def test_emulator_builds_and_exports_the_abi():
+    backend.build()
+    h = ctypes.CDLL(backend.LIB)
+    import genfft_b200
+    assert not [s for s in genfft_b200.exported_symbols() if not hasattr(h, s)]
+    assert hasattr(h, "genfft_emu_fiber_switches")
+
+
+def test_product_never_loads_the_emulator(monkeypatch):
+    """genfft_b200 has no CPU path: pointing its loader at the emulator is refused."""
+    backend.build()
+    from genfft_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", backend.LIB)
+    with pytest.raises(_lib.GenfftCudaError, match="emulator"):
+        _lib.lib()
+    # and the product library itself carries no emulator code
+    real = os.path.join(ROOT, "genfft_b200", "lib", "libgenfft_cuda.so")
+    if os.path.exists(real):
+        assert not hasattr(ctypes.CDLL(real), "genfft_emu_fiber_switches")
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "genfft_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "tests.emu" not in src and "libgenfft_emu" not in src and "from emu" not in src, f
+
+
+def test_gpu_suite_on_the_emulator():
+    backend.build()
+    env = dict(os.environ, GENFFT_TEST_BACKEND="emu")
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-n", str(min(8, os.cpu_count() or 1)), "-p", "no:cacheprovider"]
+    cmd += [os.path.join(ROOT, "tests", f) for f in GPU_TEST_FILES]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = r.stdout[-4000:] + r.stderr[-2000:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 400, tail

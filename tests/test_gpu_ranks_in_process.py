@@ -1,0 +1,123 @@
+"""The distributed transforms' LOCAL kernels with several ranks played by one process on one device.
+
+CudaSlabEngine's peer-storing passes (dist_rows / dist_cols with out_peers: the fused all-to-all of DistFFT2D's p2p
+transport, genfft_b200/dist.py) only need the peers' buffer addresses.  Here all P ranks' buffers live on the same
+device and the ranks run one after another, in the order DistFFT2D.transform / DistFFT1D.transform issue the phases,
+so the scatter addressing for P = 2, 4, 8 is checked on a single GPU (and, through tests/test_emu_suite.py, on the
+kernel-logic emulator without any GPU).  The multi-process path proper is tests/test_gpu_dist.py.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from genfft_b200.dist import CudaSlabEngine, four_step_shape  # noqa: E402
+
+TCPX = {np.float32: torch.complex64, np.float64: torch.complex128}
+NCPX = {np.float32: np.complex64, np.float64: np.complex128}
+
+
+def rand_c(rng, shape, dt):
+    return (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(NCPX[dt])
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("w,h", [(8, 8), (64, 16), (256, 512), (1024, 64), (32768, 8)])
+@pytest.mark.parametrize("inv", [False, True])
+def test_fft2d_slabs_p2p(dt, world, w, h, inv):
+    if w % world or h % world:
+        pytest.skip("shape not divisible by the number of ranks")
+    rng = np.random.default_rng(w * 31 + h)
+    x = rand_c(rng, (h, w), dt)
+    hl, wp = h // world, w // world
+    eng = [CudaSlabEngine(w, h, world, dt) for _ in range(world)]
+    slabs = [torch.from_numpy(x[r * hl:(r + 1) * hl]).cuda() for r in range(world)]
+    blocks = [torch.full((h, wp), float("nan"), dtype=TCPX[dt], device="cuda") for _ in range(world)]
+    outs = [torch.full((hl, w), float("nan"), dtype=TCPX[dt], device="cuda") for _ in range(world)]
+    for r in range(world):  # rows + transpose 1: every rank stores into every peer's (H x W/P) block
+        eng[r].rows_to_peers(slabs[r], [b.data_ptr() for b in blocks], r, inv)
+    torch.cuda.synchronize()
+    for r in range(world):  # columns + transpose 2: back to row slabs, natural order
+        eng[r].cols_to_peers(blocks[r].data_ptr(), [o.data_ptr() for o in outs], r, inv)
+    torch.cuda.synchronize()
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    x64 = x.astype(np.complex128)
+    want = np.fft.ifft2(x64) * (w * h) if inv else np.fft.fft2(x64)
+    assert oracle.rel_l2(got, want) <= oracle.tolerance(w * h, dt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("w,h", [(64, 16), (512, 256)])
+def test_fft2d_slabs_packed_transport(dt, world, w, h):
+    """The NCCL transport's local kernels: rows_pack -> (all-to-all played by a host permutation) -> cols -> unpack."""
+    rng = np.random.default_rng(w + h)
+    x = rand_c(rng, (h, w), dt)
+    hl, wp = h // world, w // world
+    eng = [CudaSlabEngine(w, h, world, dt) for _ in range(world)]
+    sends = []
+    for r in range(world):
+        send = eng[r].empty(world, hl, wp)
+        eng[r].rows_pack(torch.from_numpy(x[r * hl:(r + 1) * hl]).cuda(), send, False)
+        sends.append(send)
+    torch.cuda.synchronize()
+    outs2 = []
+    for g in range(world):  # all_to_all_single: rank g receives block g of every rank
+        block = torch.cat([sends[r][g] for r in range(world)], dim=0).contiguous()
+        bo = eng[g].empty(h, wp)
+        eng[g].cols(bo, block, False)
+        outs2.append(bo)
+    torch.cuda.synchronize()
+    got_t = np.concatenate([o.cpu().numpy() for o in outs2], axis=1)  # transposed-output mode: (H x W) by column blocks
+    want = np.fft.fft2(x.astype(np.complex128))
+    assert oracle.rel_l2(got_t, want) <= oracle.tolerance(w * h, dt)
+    for r in range(world):  # second all-to-all + unpack into the natural-order row slab
+        recv = torch.stack([outs2[g][r * hl:(r + 1) * hl] for g in range(world)], dim=0).contiguous()
+        out = eng[r].empty(hl, w)
+        eng[r].unpack(out, recv)
+        torch.cuda.synchronize()
+        assert oracle.rel_l2(out.cpu().numpy(), want[r * hl:(r + 1) * hl]) <= oracle.tolerance(w * h, dt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("lg", [6, 11, 16])
+@pytest.mark.parametrize("inv", [False, True])
+def test_four_step_1d_p2p(dt, world, lg, inv):
+    """DistFFT1D's p2p phases (strided peer copy, column pass + scatter, twiddle, row pass + scatter, transpose)."""
+    n = 1 << lg
+    h, w = four_step_shape(n, world)
+    hl, wp = h // world, w // world
+    rng = np.random.default_rng(lg)
+    x = rand_c(rng, n, dt)
+    eng = [CudaSlabEngine(w, h, world, dt) for _ in range(world)]
+    slabs = [torch.from_numpy(x[r * hl * w:(r + 1) * hl * w].reshape(hl, w)).cuda() for r in range(world)]
+    blocks = [torch.full((h, wp), float("nan"), dtype=TCPX[dt], device="cuda") for _ in range(world)]
+    mids = [torch.full((hl, w), float("nan"), dtype=TCPX[dt], device="cuda") for _ in range(world)]
+    blocks2 = [torch.full((h, wp), float("nan"), dtype=TCPX[dt], device="cuda") for _ in range(world)]
+    for r in range(world):  # transpose 1: row slabs -> column blocks
+        eng[r].cols_blocks_to_peers(slabs[r], [b.data_ptr() for b in blocks], r)
+    torch.cuda.synchronize()
+    for r in range(world):  # length-H column transforms, scattered back to row slabs (rows = kr)
+        eng[r].cols_to_peers(blocks[r].data_ptr(), [m.data_ptr() for m in mids], r, inv)
+    torch.cuda.synchronize()
+    for r in range(world):  # W_n^(kr c), then length-W row transforms scattered to column blocks Z[kr][kc]
+        eng[r].twiddle(mids[r], r * hl, inv)
+        eng[r].rows_to_peers(mids[r], [b.data_ptr() for b in blocks2], r, inv)
+    torch.cuda.synchronize()
+    x64 = x.astype(np.complex128)
+    want = np.fft.ifft(x64) * n if inv else np.fft.fft(x64)
+    z = np.concatenate([b.cpu().numpy() for b in blocks2], axis=1)  # Z[kr][kc] = X[kr + H kc]
+    assert oracle.rel_l2(z, want.reshape(w, h).T) <= oracle.tolerance(n, dt)
+    outs = []
+    for r in range(world):  # natural order: rank r holds X[r n/P : (r+1) n/P] = rows kc of Z^T
+        out = eng[r].empty(wp, h)
+        eng[r].transpose(out, blocks2[r])
+        outs.append(out)
+    torch.cuda.synchronize()
+    got = np.concatenate([o.cpu().numpy().reshape(-1) for o in outs])
+    assert oracle.rel_l2(got, want) <= oracle.tolerance(n, dt)

@@ -7,7 +7,10 @@
 #include <sys/mman.h>
 #include <ucontext.h>
 
+#include <unistd.h>
+
 #include <cstdio>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -42,6 +45,40 @@ void fiber_entry() {
 }  // namespace
 
 unsigned char* dyn_smem() { return g_smem; }
+
+namespace {
+std::mutex g_alloc_mu;
+std::map<void*, std::pair<void*, size_t>> g_allocs;  // user pointer -> (mapping, length)
+}
+
+void* guarded_alloc(size_t bytes) {
+  const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+  const size_t body = ((bytes ? bytes : 1) + 15) & ~(size_t)15;
+  const size_t body_pages = (body + page - 1) / page * page;
+  const size_t len = body_pages + 2 * page;
+  void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (m == MAP_FAILED) return nullptr;
+  unsigned char* base = static_cast<unsigned char*>(m);
+  mprotect(base, page, PROT_NONE);
+  mprotect(base + page + body_pages, page, PROT_NONE);
+  unsigned char* user = base + page + body_pages - body;
+  memset(base + page, 0xCD, body_pages);  // poison: reading what nothing wrote shows up as garbage, as on the device
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  g_allocs[user] = {m, len};
+  return user;
+}
+
+void guarded_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  auto it = g_allocs.find(p);
+  if (it == g_allocs.end()) {
+    fprintf(stderr, "genfft_emu: cudaFree of a pointer cudaMalloc did not return\n");
+    abort();
+  }
+  munmap(it->second.first, it->second.second);
+  g_allocs.erase(it);
+}
 
 int num_sms() {
   const char* s = getenv("GENFFT_EMU_SMS");

@@ -99,17 +99,18 @@ namespace genfft_emu {
 int num_sms();  // GENFFT_EMU_SMS (default 3): small, so that persistent grids have several CTAs but stay cheap
 }
 
+// Device allocations sit between two inaccessible guard pages with their END on the upper guard (16-byte granular),
+// so a kernel that runs past (or before) an allocation it was given faults immediately -- a poor man's memcheck.
+namespace genfft_emu {
+void* guarded_alloc(size_t bytes);
+void guarded_free(void* p);
+}
 inline cudaError_t cudaMalloc(void** p, size_t bytes) {
-  *p = nullptr;
-  if (bytes == 0) bytes = 1;
-  void* q = nullptr;
-  if (posix_memalign(&q, 256, bytes) != 0) return cudaErrorMemoryAllocation;
-  memset(q, 0xCD, bytes);  // poison: a kernel that reads what nothing wrote shows up as garbage, as on the device
-  *p = q;
-  return cudaSuccess;
+  *p = ::genfft_emu::guarded_alloc(bytes);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc(reinterpret_cast<void**>(p), bytes); }
-inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) { ::genfft_emu::guarded_free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,

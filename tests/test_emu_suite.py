@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from emu import backend  # noqa: E402
 
 GPU_TEST_FILES = ["test_gpu_c2c.py", "test_gpu_real_vert_2d.py", "test_gpu_chain.py", "test_gpu_random_sweep.py",
-                  "test_gpu_dist_kernels.py", "test_gpu_ranks_in_process.py"]
+                  "test_gpu_dist_kernels.py", "test_gpu_zz_ranks_in_process.py"]
 
 
 def test_emulator_builds_and_exports_the_abi():
@@ -61,3 +61,17 @@ def test_gpu_suite_on_the_emulator():
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
     assert m and int(m.group(1)) >= 400, tail
+
+
+@pytest.mark.parametrize("binary", ["tests/cpp/_build/test_mirror", "oracle/_ref/ref_plugin_test"])
+def test_cpp_layers_on_the_emulator(binary):
+    """The C++ class mirror (include/genfft_cuda/fft.h) and the reference's own classes with the CUDA factories
+    (include/genfft_cuda/backend.h), i.e. the programs of tests/test_gpu_cpp.py, with the emulator's C ABI symbols
+    interposed in front of libgenfft_cuda.so's."""
+    path = os.path.join(ROOT, binary)
+    if not os.path.exists(path):
+        pytest.skip(f"{binary} was not prebuilt")
+    backend.build()
+    r = subprocess.run([path], capture_output=True, text=True, timeout=600, env=dict(os.environ, LD_PRELOAD=backend.LIB))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "PASSED" in r.stdout

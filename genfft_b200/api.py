@@ -38,6 +38,10 @@ def _precision(dtype) -> int:
     raise TypeError(f"unsupported dtype {dtype}")
 
 
+_TORCH_DTYPES = {} if torch is None else {torch.float32: (F32, 1), torch.complex64: (F32, 2),
+                                          torch.float64: (F64, 1), torch.complex128: (F64, 2)}
+
+
 class _Buf:
     """Resolved view of a user buffer: raw pointer, residency, scalar precision, length in scalars."""
 
@@ -48,10 +52,13 @@ class _Buf:
         if torch is not None and isinstance(x, torch.Tensor):
             if not x.is_contiguous():
                 raise ValueError("buffers must be contiguous")
+            info = _TORCH_DTYPES.get(x.dtype)  # (precision, scalars per element); a dict lookup: this is the C1 hot path
+            if info is None:
+                raise TypeError(f"unsupported dtype {x.dtype}")
             self.ptr = x.data_ptr()
             self.cuda = x.is_cuda
-            self.precision = _precision(x.dtype)
-            self.nscalars = x.numel() * (2 if x.is_complex() else 1)
+            self.precision = info[0]
+            self.nscalars = x.numel() * info[1]
         elif isinstance(x, np.ndarray):
             if not x.flags["C_CONTIGUOUS"]:
                 raise ValueError("buffers must be C-contiguous")
@@ -65,8 +72,16 @@ class _Buf:
             raise TypeError("expected a torch.Tensor or numpy.ndarray")
 
 
+_raw_stream = getattr(getattr(torch, "_C", None), "_cuda_getCurrentRawStream", None) if torch is not None else None
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream if torch is not None else 0
+    """The current CUDA stream's handle (launches are asynchronous on it, like any torch op)."""
+    if torch is None:
+        return 0
+    if _raw_stream is not None:  # ~0.3 us instead of ~1.5 us for building a torch.cuda.Stream object per call
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _pair(out, inp, precision):

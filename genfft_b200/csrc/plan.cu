@@ -59,9 +59,61 @@ static int ilog2(long long n) {
   return l;
 }
 
+// Run-time knobs (GENFFT_CUDA_*) are consulted on every execution so that a caller can change
+// them between calls.  getenv() is a linear scan of the whole environment (~0.3 us with ~130 entries), and one exec call
+// consults eight knobs -- more host time than the launch of a small transform costs (C1).  So the GENFFT_CUDA_*
+// entries are collected into a per-thread snapshot that is revalidated (identity of the environment's entry
+// pointers: setenv / putenv / unsetenv all replace or move them) once per KnobScope, i.e. once per execution.
+extern "C" char** environ;
+namespace {
+struct KnobSnapshot {
+  char** env = nullptr;
+  size_t count = 0;
+  uintptr_t sig = 0;
+  std::vector<const char*> entries;  // "GENFFT_CUDA_<NAME>=<value>" strings
+  uint64_t knob_hash = 0;            // of the entries' text: what a cached launch decision depends on
+  int depth = 0;
+  bool valid = false;
+};
+thread_local KnobSnapshot t_knobs;
+
+void knobs_validate() {
+  KnobSnapshot& k = t_knobs;
+  char** e = environ;
+  size_t n = 0;
+  uintptr_t sig = 0;
+  if (e)
+    for (; e[n]; n++) sig += reinterpret_cast<uintptr_t>(e[n]) ^ (uintptr_t)n;
+  if (k.valid && k.env == e && k.count == n && k.sig == sig) return;
+  k.entries.clear();
+  k.knob_hash = 1469598103934665603ull;
+  for (size_t i = 0; i < n; i++)
+    if (e[i][0] == 'G' && strncmp(e[i], "GENFFT_CUDA_", 12) == 0) {
+      k.entries.push_back(e[i]);
+      for (const char* c = e[i]; *c; c++) k.knob_hash = (k.knob_hash ^ (unsigned char)*c) * 1099511628211ull;
+      k.knob_hash = (k.knob_hash ^ 0xffu) * 1099511628211ull;
+    }
+  k.env = e;
+  k.count = n;
+  k.sig = sig;
+  k.valid = true;
+}
+
+// every function that reads knobs at execution time opens a scope; only the outermost one revalidates
+struct KnobScope {
+  KnobScope() {
+    if (t_knobs.depth++ == 0) knobs_validate();
+  }
+  ~KnobScope() { t_knobs.depth--; }
+};
+}  // namespace
+
 static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s && *s ? atoi(s) : dflt;
+  if (t_knobs.depth == 0) knobs_validate();  // plan-creation-time reads
+  const size_t len = strlen(name);
+  for (const char* ent : t_knobs.entries)
+    if (strncmp(ent, name, len) == 0 && ent[len] == '=') return ent[len + 1] ? atoi(ent + len + 1) : dflt;
+  return dflt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -534,7 +586,11 @@ static void set_tile_divisors(PassParams& p) {
   p.n2_shr = d2.shr;
 }
 
-static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p, cudaStream_t stream) {
+// Everything a pass launch decides before the launch itself: the compiled mode, the grid, the tile divisors.
+static int resolve_pass(const Plan* plan, const PassSpec& ps, const PassParams& p, ResolvedLaunch* r) {
+  KnobScope knob_scope;
+  r->grid = 0;
+  r->launch = nullptr;
   if (p.ntiles == 0) return GENFFT_CUDA_OK;
   int mode = p.mode;
   const int inv = p.inverse ? 1 : 0;
@@ -557,20 +613,51 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
   const bool frac = p.grid_frac > 0.f && p.grid_frac < 1.f;
   if (frac) cap = std::max<long long>(1, (long long)(cap * p.grid_frac));
   const bool persistent = frac || env_int("GENFFT_CUDA_PERSISTENT", 0);
-  PassParams q = p;
+  r->q = p;
+  PassParams& q = r->q;
   set_tile_divisors(q);
-  int grid;
   if (persistent) {
     q.tiles_per_cta = 0;
-    grid = (int)std::min<long long>(p.ntiles, cap);
+    r->grid = (int)std::min<long long>(p.ntiles, cap);
   } else {
     q.tiles_per_cta = mode == M_ROWTMA ? (uint32_t)std::max(1, env_int("GENFFT_CUDA_TMA_TILES", 8)) : 1u;
-    grid = (int)std::min<long long>(((long long)p.ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta, 0x7fffffffLL);
+    r->grid = (int)std::min<long long>(((long long)p.ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta, 0x7fffffffLL);
   }
-  ps.k->launch[mode][inv](q, grid, stream);
+  r->launch = ps.k->launch[mode][inv];
+  return GENFFT_CUDA_OK;
+}
+
+static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p, cudaStream_t stream) {
+  ResolvedLaunch r;
+  int rc = resolve_pass(plan, ps, p, &r);
+  if (rc) return rc;
+  if (!r.launch) return GENFFT_CUDA_OK;
+  r.launch(r.q, r.grid, stream);
   g_launches++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
+}
+
+// Resolves the launches of a single-pass c2c_1d plan once (FastPath, plan.h): the per-execution host work of the
+// general driver below (pass list, buffer assignment, chain search, knob lookups, occupancy lookup) costs more than
+// launching a small transform (C1: N = 1024) does.
+static void build_fast_path(Plan* p) {
+  p->fast.valid = false;
+  if (p->kind != PLAN_C2C_1D || p->seq.passes.size() != 1) return;
+  if (p->grid_frac[0] < 1.f || p->grid_frac[1] < 1.f) return;
+  KnobScope knob_scope;
+  const PassSpec& ps = p->seq.passes[0];
+  for (int inv = 0; inv < 2; inv++)
+    for (int al = 0; al < 2; al++) {
+      // stand-in input pointers: only their alignment enters the decisions (TMA prefetch needs 16 bytes)
+      const void* in = reinterpret_cast<const void*>((uintptr_t)(al ? 4096 : 4096 + 8));
+      PassParams pp = emit_1d(ps, p->n, in, p->in_dist, nullptr, p->out_dist, p->batch, inv, false);
+      pp.grid_frac = p->grid_frac[1];
+      ResolvedLaunch& r = p->fast.rl[inv][al];
+      if (resolve_pass(p, ps, pp, &r) != GENFFT_CUDA_OK || !r.launch) return;
+    }
+  p->fast.knob_hash = t_knobs.knob_hash;
+  p->fast.valid = true;
 }
 
 // One launch for two consecutive passes with the intermediate kept in L2 (chain_kernel.cuh).
@@ -701,6 +788,7 @@ struct Step {
 };
 
 static void seq_steps(const Seq& seq, bool col, std::vector<Step>& steps, bool brev_first, bool real_first) {
+  KnobScope knob_scope;
   const size_t m = seq.passes.size();
   for (size_t s = 0; s < m; s++) {
     Step st;
@@ -737,6 +825,7 @@ struct DitFuse {
 static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, long long scratch_pitch,
                      size_t scratch_elems, long long count, long long cols, int inverse, cudaStream_t stream,
                      const FinalStore* fs = nullptr, const DitFuse* df = nullptr, const void* in2 = nullptr) {
+  KnobScope knob_scope;
   std::vector<Step> steps(steps_in);
   if (fs && steps.size() > 1) steps.back().safe = false;  // the last pass writes elsewhere than it reads
   const size_t es = elem_size(plan->precision);
@@ -1078,6 +1167,7 @@ int genfft_cuda_plan_c2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
     delete p;
     return rc;
   }
+  build_fast_path(p);
   *plan = static_cast<genfft_cuda_plan_t>(p);
   return GENFFT_CUDA_OK;
 }
@@ -1170,6 +1260,7 @@ int genfft_cuda_plan_set_grid_fraction(genfft_cuda_plan_t plan, double frac_othe
     return fail(GENFFT_CUDA_ERR_ARG, "fractions must be in (0, 1]");
   plan->grid_frac[0] = (float)frac_other;
   plan->grid_frac[1] = (float)frac_last;
+  build_fast_path(plan);  // cached launches were resolved for full grids
   return GENFFT_CUDA_OK;
 }
 
@@ -1233,6 +1324,7 @@ int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
 
 int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStream_t stream, bool brev, bool real_in,
                       long long batch, const void* in2) {
+  KnobScope knob_scope;
   if (!p || p->kind != PLAN_C2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (batch < 0) batch = p->batch;
@@ -1250,6 +1342,19 @@ int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStrea
     if (in2) return fail(GENFFT_CUDA_ERR_SIZE, "transform_interleave needs n >= 2");
     return launch_copy(p->precision, cp, 1, stream);
   }
+  // single pass, plain complex input, the plan's own batch, knobs unchanged since plan creation: the launch was
+  // resolved when the plan was made (identical to what the general driver below would decide)
+  if (p->fast.valid && !brev && !real_in && !in2 && batch == p->batch && (out != in || p->in_dist == p->out_dist) &&
+      p->fast.knob_hash == t_knobs.knob_hash) {
+    const ResolvedLaunch& r = p->fast.rl[inverse ? 1 : 0][(reinterpret_cast<uintptr_t>(in) % 16 == 0) ? 1 : 0];
+    PassParams q = r.q;
+    q.in = in;
+    q.out = out;
+    r.launch(q, r.grid, stream);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return GENFFT_CUDA_OK;
+  }
   std::vector<Step> steps;
   seq_steps(p->seq, false, steps, brev, real_in);
   View vin{const_cast<void*>(in), p->in_dist}, vout{out, p->out_dist};
@@ -1263,6 +1368,7 @@ int exec_r2c_internal(Plan* p, void* out, const void* in, cudaStream_t st, long 
 // in_dist (real scalars) / out_dist (complex elements) override the plan's when non-zero (rows of a real image)
 int exec_r2c_strided(Plan* pl, void* out, const void* in, cudaStream_t st, long long batch, long long in_dist_o,
                      long long out_dist_o) {
+  KnobScope knob_scope;
   if (!pl || (pl->kind != PLAN_R2C_1D && pl->kind != PLAN_R2C_2D)) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c plan");
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (batch < 0) batch = pl->batch;
@@ -1434,6 +1540,7 @@ int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_
 // with GENFFT_CUDA_2X_FUSED=0, one interleaving copy into plan-owned memory precedes the ordinary 2D pass chain.
 int genfft_cuda_exec_r2c_2d_2x_dev(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in1,
                                    int64_t in_stride1, const void* in2, int64_t in_stride2, void* stream) {
+  KnobScope knob_scope;
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_2D) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
   if (!out || !in1 || !in2) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");

@@ -29,6 +29,21 @@ struct Seq {
   bool wide = false;             // built for column (strided) use
 };
 
+// A pass launch with every decision taken (mode, grid, tile divisors); only the buffers remain to be filled in.
+struct ResolvedLaunch {
+  PassParams q;
+  int grid = 0;
+  void (*launch)(const PassParams& prm, int grid, cudaStream_t stream) = nullptr;
+};
+
+// Single-pass contiguous transforms (c2c_1d with n on chip: C1, C2) resolved at plan creation, so that an execution is
+// two pointer stores and the launch.  [inverse][input 16-byte aligned (TMA prefetch eligible)]
+struct FastPath {
+  bool valid = false;
+  uint64_t knob_hash = 0;  // of the GENFFT_CUDA_* environment the decisions were taken under
+  ResolvedLaunch rl[2][2];
+};
+
 struct Plan {
   PlanKind kind;
   int precision;
@@ -65,6 +80,7 @@ struct Plan {
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t events[8] = {};
   bool streams_ready = false;
+  FastPath fast;
 };
 
 }  // namespace genfft_cuda

@@ -272,3 +272,42 @@ def test_sizes_beyond_the_reference_maximum(lg, dt):
     plan.inverse(z, y)
     err = (z / n - x).abs().max().item()
     assert err < (1e-4 if dt == np.float32 else 1e-12), plan.describe()
+
+
+@pytest.mark.parametrize("dt,n,batch", [(np.float32, 1024, 1), (np.float32, 4096, 700), (np.float32, 16, 5),
+                                        (np.float64, 256, 1000), (np.float64, 8192, 3)])
+def test_cached_launch_matches_the_general_driver(dt, n, batch):
+    """Single-pass plans resolve their launch at plan creation (FastPath, plan.h); an execution under a changed
+    GENFFT_CUDA_* environment goes through the general pass driver instead.  Both must launch the same kernel on the
+    same grid: bit-identical output and one launch each -- forward, inverse, in place, and from an input that is only
+    8-byte aligned (no TMA prefetch)."""
+    import os
+    tdt = torch.complex64 if dt == np.float32 else torch.complex128
+    rng = np.random.default_rng(n + batch)
+    x = torch.from_numpy(rand_cpx(rng, batch * n + 1, dt)).cuda()
+    plan = g.FFT(n, dt, batch=batch)
+
+    def run(off, inv, in_place=False):
+        buf = torch.empty(batch * n + 1, dtype=tdt, device="cuda")
+        src = buf[off:off + batch * n]  # off = 1: the input is only 8-byte aligned in float
+        src.copy_(x[:batch * n])
+        assert src.data_ptr() % 16 == (8 * off if dt == np.float32 else 0)
+        dst = src if in_place else torch.empty(batch * n, dtype=tdt, device="cuda")
+        n0 = g.launch_count()
+        plan.transform(dst, src, inv)
+        torch.cuda.synchronize()
+        assert g.launch_count() - n0 == 1
+        return dst.clone()
+
+    for off in (0, 1) if dt == np.float32 else (0,):
+        for inv in (False, True):
+            for in_place in (False, True):
+                fast = run(off, inv, in_place)
+                os.environ["GENFFT_CUDA_UNRELATED_KNOB"] = "1"  # any change of the knob environment bypasses the cache
+                try:
+                    general = run(off, inv, in_place)
+                finally:
+                    del os.environ["GENFFT_CUDA_UNRELATED_KNOB"]
+                assert torch.equal(fast, general)
+    want = np.fft.fft(x[:batch * n].cpu().numpy().reshape(batch, n).astype(np.complex128), axis=1)
+    assert oracle.rel_l2(run(0, False).cpu().numpy().reshape(batch, n), want) <= oracle.tolerance(n, dt)

@@ -22,7 +22,12 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, "_build", "libgenfft_emu.so")
+# GENFFT_EMU_VARIANT=<name>:<extra compiler flags> selects a compile-time variant of the kernel sources, built into
+# _build_<name>/ (e.g. "packed:-DGENFFT_PACKED_F32=1": the formulas of the packed-pair variant with scalar arithmetic)
+_VARIANT = os.environ.get("GENFFT_EMU_VARIANT", "")
+_VNAME, _, _VFLAGS = _VARIANT.partition(":")
+BUILD_DIR = os.path.join(HERE, "_build_" + _VNAME if _VNAME else "_build")
+LIB = os.path.join(BUILD_DIR, "libgenfft_emu.so")
 
 
 def sources() -> list[str]:
@@ -40,7 +45,8 @@ def stale() -> bool:
 
 def build(force: bool = False) -> None:
     if force or stale():
-        subprocess.run(["bash", os.path.join(HERE, "build.sh")], check=True, stdout=subprocess.DEVNULL)
+        env = dict(os.environ, GENFFT_EMU_OUT=BUILD_DIR, GENFFT_EMU_EXTRA=_VFLAGS)
+        subprocess.run(["bash", os.path.join(HERE, "build.sh")], check=True, stdout=subprocess.DEVNULL, env=env)
 
 
 def load() -> C.CDLL:

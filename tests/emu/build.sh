@@ -4,11 +4,11 @@
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 SRC="$HERE/../../genfft_b200/csrc"
-OUT="$HERE/_build"
+OUT="${GENFFT_EMU_OUT:-$HERE/_build}"
 OBJ="$OUT/obj"
 mkdir -p "$OBJ"
 CXX=${CXX:-g++}
-FLAGS="-std=c++17 ${GENFFT_EMU_OPT:--O1} -fPIC -DGENFFT_EMU=1 -I$HERE/shim -Wno-unknown-pragmas -Wno-attributes -x c++"
+FLAGS="-std=c++17 ${GENFFT_EMU_OPT:--O1} $GENFFT_EMU_EXTRA -fPIC -DGENFFT_EMU=1 -I$HERE/shim -Wno-unknown-pragmas -Wno-attributes -x c++"
 pids=()
 for k in 0 1 2 3; do
   $CXX $FLAGS -DGENFFT_CSET=$k -c "$SRC/chains_inst.cu" -o "$OBJ/chains_$k.o" & pids+=($!)

@@ -75,3 +75,18 @@ def test_cpp_layers_on_the_emulator(binary):
     r = subprocess.run([path], capture_output=True, text=True, timeout=600, env=dict(os.environ, LD_PRELOAD=backend.LIB))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "PASSED" in r.stdout
+
+
+def test_packed_pair_variant_on_the_emulator():
+    """The compile-time variant GENFFT_PACKED_F32 (csrc/radix.cuh: FADD2 / FFMA2 on register pairs, waiting for its
+    A/B measurement) rewrites the real-FFT split in terms of pair operations.  Its formulas are checked here with the
+    pair operations in their scalar form; the PTX spelling itself only a GPU can check (tools/round_start.sh)."""
+    env = dict(os.environ, GENFFT_TEST_BACKEND="emu", GENFFT_EMU_VARIANT="packed:-DGENFFT_PACKED_F32=1")
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-n", str(min(8, os.cpu_count() or 1)), "-p", "no:cacheprovider",
+           "-k", "real_fft_vs_reference or r2c_c2r_random", os.path.join(ROOT, "tests", "test_gpu_real_vert_2d.py"),
+           os.path.join(ROOT, "tests", "test_gpu_random_sweep.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = r.stdout[-4000:] + r.stderr[-2000:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 20, tail

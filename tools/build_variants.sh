@@ -1,0 +1,11 @@
+#!/bin/bash
+# Builds the compile-time variants of libgenfft_cuda that are waiting for an A/B measurement into
+# genfft_b200/lib_exp_<name>/ (git-ignored, travels to the GPU box).  Run HERE (no GPU needed), then on the box:
+#   python tools/variant_bench.py lib,lib_exp_packed c2 c3f c4 c5
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$HERE/.."
+# packed single-precision adds (FADD2 on register pairs, radix.cuh): 14-20 % fewer instructions per tile, bit-identical
+GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed" GENFFT_NVCC_EXTRA="-DGENFFT_PACKED_F32=1" bash "$ROOT/genfft_b200/csrc/build.sh"
+# ... and with the two-instruction packed complex multiply (more shuffles, spills in the twiddled column passes)
+GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed2" GENFFT_NVCC_EXTRA="-DGENFFT_PACKED_F32=2" bash "$ROOT/genfft_b200/csrc/build.sh"

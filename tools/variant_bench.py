@@ -14,6 +14,9 @@ which = sys.argv[2:]
 for name in libs:
     _lib._lib = None
     _lib.LIB_PATH = os.path.join(ROOT, "genfft_b200", name, "libgenfft_cuda.so")
+    if not os.path.exists(_lib.LIB_PATH):
+        print(f"== {name}: not built (tools/build_variants.sh)", flush=True)
+        continue
     print(f"== {name}", flush=True)
     if "c3" in which:
         q.c2c(1 << 24, 1, np.float64)

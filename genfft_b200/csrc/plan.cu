@@ -328,27 +328,34 @@ static int stage_twiddle_table(int device, int precision, const KernelEntry* k, 
   return GENFFT_CUDA_OK;
 }
 
-// inter-pass factor W_{P*Ns}^(p*i) laid out [i][p] (see PassParams::tw_b)
-static std::map<std::tuple<int, int, int, long long>, void*> g_pass_tables;
+// inter-pass factor W_{P*Ns}^(p*i) laid out [i][p] (see PassParams::tw_b); with -DGENFFT_TWB_TILED tile-major
+// [p / C][i][p % C] for the C-column tiles of the kernel that reads it: a thread's P-1 entries are then immediate
+// offsets i*C from one address, and the rows a warp reads are adjacent cache lines
+static std::map<std::tuple<int, int, int, long long, int>, void*> g_pass_tables;
 
-static int pass_stage_table(int device, int precision, int P, long long Ns, const void** out) {
+static int pass_stage_table(int device, int precision, int P, long long Ns, int C, const void** out) {
   std::lock_guard<std::mutex> lk(g_tw_mu);
-  auto key = std::make_tuple(device, precision, P, Ns);
+  auto key = std::make_tuple(device, precision, P, Ns, C);
   auto it = g_pass_tables.find(key);
   if (it != g_pass_tables.end()) {
     *out = it->second;
     return GENFFT_CUDA_OK;
   }
   const size_t es = elem_size(precision);
-  const size_t count = (size_t)P * (size_t)Ns;
-  std::vector<unsigned char> host(es * count);
-  // row i is W_{P*Ns}^(p*i): fill row 1 exactly, the others by exact index arithmetic (p*i mod P*Ns)
+  const size_t ntiles = (size_t)((Ns + C - 1) / C);
+  const size_t count = ntiles * (size_t)P * (size_t)C;
+  std::vector<unsigned char> host(es * count, 0);
+  // entry (i, p) is W_{P*Ns}^(p*i), by exact index arithmetic (p*i mod P*Ns); columns beyond Ns in the last tile stay 0
   const unsigned long long M = (unsigned long long)P * (unsigned long long)Ns;
   for (int i = 0; i < P; i++)
     for (long long q = 0; q < Ns; q++) {
       long double c, sn;
       unit_root(((unsigned long long)q * (unsigned long long)i) % M, M, &c, &sn);
+#ifdef GENFFT_TWB_TILED
+      const size_t e = (size_t)(q / C) * (size_t)P * (size_t)C + (size_t)i * (size_t)C + (size_t)(q % C);
+#else
       const size_t e = (size_t)i * (size_t)Ns + (size_t)q;
+#endif
       if (precision == GENFFT_CUDA_F32) {
         float* t = reinterpret_cast<float*>(host.data()) + 2 * e;
         t[0] = (float)c;
@@ -423,8 +430,8 @@ static int build_seq(Seq* seq, int device, int precision, long long N, bool wide
     if (Ns > 1) {
       rc = two_level_table(device, precision, Ns * ps.R, &ps.tw_hi, &ps.tw_lo, &ps.tw_shift);
       if (rc) return rc;
-      // W_{P*Ns}^(p*i), i < P, p < Ns, laid out [i][p]
-      rc = pass_stage_table(device, precision, ps.k->P, Ns, &ps.tw_b);
+      // W_{P*Ns}^(p*i), i < P, p < Ns
+      rc = pass_stage_table(device, precision, ps.k->P, Ns, ps.k->C, &ps.tw_b);
       if (rc) return rc;
     }
     seq->passes.push_back(ps);

@@ -57,7 +57,8 @@ struct PassParams {
   long long g_t1, g_c, g_i, brev_stride;
   // inter-pass Stockham twiddle W_M^(p*idx), M = Ns*L, p = t1*p_t1 + col*p_c, idx = u + i*TN, factored as
   //   W_M^(p*u)            one per thread, two-level table:  tw_hi[e >> tw_shift] * tw_lo[e & mask], e = p*u
-  //   W_M^(p*i*TN)         = W_{P*Ns}^(p*i), table tw_b[i*tw_b_stride + p] (lanes read consecutive p: coalesced)
+  //   W_M^(p*i*TN)         = W_{P*Ns}^(p*i), table tw_b[i*tw_b_stride + p] (lanes read consecutive p: coalesced); with
+  //                          GENFFT_TWB_TILED tile-major [p / C][i][p % C] (a thread's entries at immediate offsets i*C)
   const void* tw_hi;
   const void* tw_lo;
   int tw_shift;
@@ -340,11 +341,19 @@ struct TileKernel {
     V ah = __ldg(hi + (e >> prm.tw_shift));
     V al = __ldg(lo + (e & ((1u << prm.tw_shift) - 1u)));
     const cpx<T> a = cmul(cpx<T>(ah.x, ah.y), cpx<T>(al.x, al.y));  // W_M^(p*u)
+    V b[P];
+#ifdef GENFFT_TWB_TILED
+    // variant: tile-major table [p / C][i][p % C], the P-1 loads are immediate offsets from one address
+    // (-4.6 % instructions in this pass, waiting for its A/B: tools/build_variants.sh)
+    const V* tb = reinterpret_cast<const V*>(prm.tw_b) + ((p / (uint32_t)C) * (uint32_t)(P * C) + (p % (uint32_t)C));
+#pragma unroll
+    for (int i = 1; i < P; i++) b[i] = __ldg(tb + i * C);
+#else
     const V* tb = reinterpret_cast<const V*>(prm.tw_b) + p;
     const uint32_t ts32 = (uint32_t)prm.tw_b_stride;
-    V b[P];
 #pragma unroll
     for (int i = 1; i < P; i++) b[i] = ldg_strided(tb, ts32, (uint32_t)i);
+#endif
     x[0] = cmul(x[0], a);
 #pragma unroll
     for (int i = 1; i < P; i++) x[i] = cmul(x[i], cmul(a, cpx<T>(b[i].x, b[i].y)));

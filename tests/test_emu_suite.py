@@ -77,11 +77,13 @@ def test_cpp_layers_on_the_emulator(binary):
     assert "PASSED" in r.stdout
 
 
-def test_packed_pair_variant_on_the_emulator():
-    """The compile-time variant GENFFT_PACKED_F32 (csrc/radix.cuh: FADD2 / FFMA2 on register pairs, waiting for its
-    A/B measurement) rewrites the real-FFT split in terms of pair operations.  Its formulas are checked here with the
-    pair operations in their scalar form; the PTX spelling itself only a GPU can check (tools/round_start.sh)."""
-    env = dict(os.environ, GENFFT_TEST_BACKEND="emu", GENFFT_EMU_VARIANT="packed:-DGENFFT_PACKED_F32=1")
+def test_pending_variants_on_the_emulator():
+    """The compile-time variants that wait for their A/B measurement (tools/build_variants.sh): GENFFT_PACKED_F32
+    (csrc/radix.cuh: FADD2 / FFMA2 on register pairs; it rewrites the real-FFT split in terms of pair operations) and
+    GENFFT_TWB_TILED (tile-major inter-pass twiddle table, host and device side).  Their index arithmetic and formulas
+    are checked here, the pair operations in their scalar form; the PTX spelling itself only a GPU can check
+    (tools/round_start.sh runs the GPU tests against the variant library)."""
+    env = dict(os.environ, GENFFT_TEST_BACKEND="emu", GENFFT_EMU_VARIANT="packed:-DGENFFT_PACKED_F32=1 -DGENFFT_TWB_TILED=1")
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-n", str(min(8, os.cpu_count() or 1)), "-p", "no:cacheprovider",
            "-k", "real_fft_vs_reference or r2c_c2r_random", os.path.join(ROOT, "tests", "test_gpu_real_vert_2d.py"),
            os.path.join(ROOT, "tests", "test_gpu_random_sweep.py")]

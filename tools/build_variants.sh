@@ -9,3 +9,5 @@ ROOT="$HERE/.."
 GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed" GENFFT_NVCC_EXTRA="-DGENFFT_PACKED_F32=1" bash "$ROOT/genfft_b200/csrc/build.sh"
 # ... and with the two-instruction packed complex multiply (more shuffles, spills in the twiddled column passes)
 GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed2" GENFFT_NVCC_EXTRA="-DGENFFT_PACKED_F32=2" bash "$ROOT/genfft_b200/csrc/build.sh"
+# packed adds + tile-major inter-pass twiddle table (immediate offsets instead of 15 computed addresses per thread)
+GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed_tw" GENFFT_NVCC_EXTRA="-DGENFFT_PACKED_F32=1 -DGENFFT_TWB_TILED=1" bash "$ROOT/genfft_b200/csrc/build.sh"

@@ -12,6 +12,6 @@ python tools/quick_bench.py c3 c4 2d > gpurun_out/quick_bench.log 2>&1; cut -c1-
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a tools/tma_tile_bench.cu -o /tmp/tma_tile_bench && timeout 30 /tmp/tma_tile_bench > gpurun_out/tma_tile_bench.log 2>&1
 # compile-time variants waiting for an A/B (built beforehand by tools/build_variants.sh; skipped when absent)
 if [ -f genfft_b200/lib_exp_packed/libgenfft_cuda.so ]; then
-  python tools/variant_bench.py lib,lib_exp_packed,lib_exp_packed2 c2 c3f c4 c5 > gpurun_out/variant_packed.log 2>&1; cut -c1-120 gpurun_out/variant_packed.log
+  python tools/variant_bench.py lib,lib_exp_packed,lib_exp_packed_tw,lib_exp_packed2 c2 c3f c4 c5 > gpurun_out/variant_packed.log 2>&1; cut -c1-120 gpurun_out/variant_packed.log
   GENFFT_CUDA_LIB=$PWD/genfft_b200/lib_exp_packed/libgenfft_cuda.so python -m pytest tests/test_gpu_c2c.py tests/test_gpu_real_vert_2d.py -m gpu -q -x > gpurun_out/pytest_packed.log 2>&1; tail -2 gpurun_out/pytest_packed.log
 fi

@@ -79,11 +79,22 @@ static int exec_batched_host(Plan* p, void* out, const void* in, size_t in_elem,
     char* din = (char*)p->stage_in + slot * in_slot;
     char* dout = (char*)p->stage_out + slot * out_slot;
     const size_t ib = (size_t)(nb - 1) * in_row + in_last, ob = (size_t)(nb - 1) * out_row + out_last;
-    HX_TRY(cudaMemcpyAsync(din, (const char*)in + (size_t)b0 * in_row, ib, cudaMemcpyHostToDevice, st));
+    // Rows are `dist` apart on both sides.  Without gaps (dist == length) a chunk is one linear copy; with gaps only
+    // the transforms themselves move: the caller's memory between two outputs is not ours to write (and the staging
+    // buffer's gaps hold nothing), the gaps of the input need not cross the bus.
+    if (in_row == in_last || nb == 1)
+      HX_TRY(cudaMemcpyAsync(din, (const char*)in + (size_t)b0 * in_row, ib, cudaMemcpyHostToDevice, st));
+    else
+      HX_TRY(cudaMemcpy2DAsync(din, in_row, (const char*)in + (size_t)b0 * in_row, in_row, in_last, (size_t)nb,
+                               cudaMemcpyHostToDevice, st));
     rc = r2c ? exec_r2c_internal(p, dout, din, st, nb)
              : exec_c2c_internal(p, brev ? din : dout, din, inverse, st, brev, real_in, nb);
     if (rc) return rc;
-    HX_TRY(cudaMemcpyAsync((char*)out + (size_t)b0 * out_row, brev ? din : dout, ob, cudaMemcpyDeviceToHost, st));
+    if (out_row == out_last || nb == 1)
+      HX_TRY(cudaMemcpyAsync((char*)out + (size_t)b0 * out_row, brev ? din : dout, ob, cudaMemcpyDeviceToHost, st));
+    else
+      HX_TRY(cudaMemcpy2DAsync((char*)out + (size_t)b0 * out_row, out_row, brev ? din : dout, out_row, out_last,
+                               (size_t)nb, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < nbuf; s++) HX_TRY(cudaStreamSynchronize(p->streams[s]));
   return GENFFT_CUDA_OK;

@@ -92,3 +92,13 @@ def test_pending_variants_on_the_emulator():
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
     assert m and int(m.group(1)) >= 20, tail
+
+
+def test_abi_fuzz_on_the_emulator():
+    """A short seeded run of tools/emu_fuzz.py: random sizes / batches / distances / strides / in-place calls through
+    every public class on host and "device" pointers, against numpy, with sentinels around the outputs and guard pages
+    behind every plan-owned allocation."""
+    backend.build()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu_fuzz.py"), "11", "250"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "cases ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

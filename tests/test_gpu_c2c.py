@@ -311,3 +311,23 @@ def test_cached_launch_matches_the_general_driver(dt, n, batch):
                 assert torch.equal(fast, general)
     want = np.fft.fft(x[:batch * n].cpu().numpy().reshape(batch, n).astype(np.complex128), axis=1)
     assert oracle.rel_l2(run(0, False).cpu().numpy().reshape(batch, n), want) <= oracle.tolerance(n, dt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_host_path_leaves_the_gaps_between_transforms_alone(dt):
+    """Batched host-pointer execution with out_dist > n: the caller's memory between two outputs is not the
+    library's to write (found by tools/emu_fuzz.py: the staged chunk used to be copied back as one linear range)."""
+    n, batch, in_dist, out_dist = 256, 13, 258, 261
+    rng = np.random.default_rng(5)
+    x = rand_cpx(rng, batch * in_dist, dt)
+    out = np.full(batch * out_dist, 7.5 - 3.25j, CPX[dt])
+    g.FFT(n, dt, batch=batch, in_dist=in_dist, out_dist=out_dist).transform(out, x)
+    got = out.reshape(batch, out_dist)
+    want = np.fft.fft(x.reshape(batch, in_dist)[:, :n].astype(np.complex128), axis=1)
+    assert oracle.rel_l2(got[:, :n], want) <= oracle.tolerance(n, dt)
+    assert np.all(got[:, n:] == 7.5 - 3.25j)
+    r = rng.uniform(-1, 1, (batch, n)).astype(dt)
+    rout = np.full((batch, n // 2 + 4), 7.5 - 3.25j, CPX[dt])
+    g.RealFFT(n, dt, half=True, batch=batch, out_dist=n // 2 + 4).forward(rout, r)
+    assert oracle.rel_l2(rout[:, :n // 2 + 1], np.fft.rfft(r.astype(np.float64), axis=1)) <= oracle.tolerance(n, dt)
+    assert np.all(rout[:, n // 2 + 1:] == 7.5 - 3.25j)

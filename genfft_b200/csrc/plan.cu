@@ -792,6 +792,7 @@ struct Step {
   bool safe;     // reads and writes the same positions per tile -> may run in place
   bool brev;
   bool real_in;
+  bool c2r = false;  // GENFFT_FUSED_C2R: the first pass builds the packed spectrum from the n/2+1 input bins while loading
 };
 
 static void seq_steps(const Seq& seq, bool col, std::vector<Step>& steps, bool brev_first, bool real_first) {
@@ -915,6 +916,17 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
     const bool peers_out = fs && fs->peers && s == n - 1;
     PassParams p = st.col ? emit_col(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev)
                           : emit_1d(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev);
+#ifdef GENFFT_FUSED_C2R
+    if (st.c2r) {
+      p.in_real = 3;
+      p.c2r_m = (uint32_t)st.N;
+      p.c2r_sc = (st.N == st.ps->R) ? 0 : 1;  // single pass: columns are transforms; first of several: columns are points
+      p.c2r_hi = plan->dit_hi;
+      p.c2r_lo = plan->dit_lo;
+      p.c2r_shift = plan->dit_shift;
+      p.mode = M_GEN;
+    }
+#endif
     if (st.real_in) {
       p.in_real = in2 ? 2 : 1;
       p.in2 = in2 ? (const char*)in2 + (size_t)off(io[s].src) * src_es : nullptr;
@@ -963,7 +975,7 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
   auto try_chain = [&](size_t sa, size_t sb, bool three, long long units, int* rc_out) -> bool {
     *rc_out = GENFFT_CUDA_OK;
     const Step &A = steps[sa], &B = steps[sb];
-    if (A.brev || A.real_in || B.brev || B.real_in) return false;
+    if (A.brev || A.real_in || A.c2r || B.brev || B.real_in || B.c2r) return false;
     if (io[sb].dst.ptr == io[sa].src.ptr) return false;
     const KernelEntry *ka = A.ps->k, *kb = B.ps->k;
     if (ka->threads != kb->threads) return false;
@@ -1622,6 +1634,17 @@ int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in,
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = p->n, M = n / 2;
   const size_t es = elem_size(p->precision);
+#ifdef GENFFT_FUSED_C2R
+  // variant: no pre-process pass and no staging -- the first butterfly pass reads X[s] and X[M - s] itself
+  if (!p->seq.passes.empty() && env_int("GENFFT_CUDA_FUSED_C2R", 1)) {
+    std::vector<Step> steps;
+    seq_steps(p->seq, false, steps, false, false);
+    steps[0].c2r = true;
+    steps[0].safe = steps[0].safe && steps.size() == 1;
+    View vin{const_cast<void*>(in), p->in_dist}, vout{out, p->out_dist / 2};
+    return run_chain(p, steps, vin, vout, M, (size_t)M * p->batch, p->batch, 0, 1, st);
+  }
+#endif
   // stage the pre-processed spectrum Z' (M complex per transform) in plan-owned memory
   {
     int rc = ensure_aux(p, (size_t)M * p->batch * es);

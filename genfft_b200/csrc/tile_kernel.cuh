@@ -76,6 +76,17 @@ struct PassParams {
   // on-chip stage twiddles, one block per radix stage s >= 1 laid out [q][p]:
   //   tw_L[stage_tw_offset(s) + q*NS + p] = W_{NS*R}^(p*q)   (lanes read consecutive p: coalesced)
   const void* tw_L;
+#ifdef GENFFT_FUSED_C2R
+  // variant (waiting for its A/B): the half-spectrum inverse's pre-process (aux_kernels.cuh c2r_pre_kernel) fused into
+  // the first pass's load, in_real == 3.  Element s of the packed spectrum is built from the bins X[s] and X[M - s] of
+  // the n/2+1 input bins: s = col*c2r_sc + idx*in_stride_i relative to the transform's first bin, which is at
+  // t.in_off (+ col*in_stride_c when the columns are whole transforms, c2r_sc == 0)
+  uint32_t c2r_m;
+  int c2r_sc;
+  const void* c2r_hi;  // two-level table of W_n^e, n = 2M
+  const void* c2r_lo;
+  int c2r_shift;
+#endif
 };
 
 __host__ __device__ constexpr int stage_radix(int L, int P, int s) {
@@ -405,6 +416,21 @@ struct TileKernel {
       if (valid) {
         if (prm.in_real == 2) {
           x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], reinterpret_cast<const T*>(prm.in2)[off]);
+#ifdef GENFFT_FUSED_C2R
+        } else if (prm.in_real == 3) {
+          // Z'[s] = (X[s] + conj X[M-s]) + i (X[s] - conj X[M-s]) conj(W_n^s)   (c2r_pre_kernel, aux_kernels.cuh)
+          const uint32_t sidx = col * (uint32_t)prm.c2r_sc + (uint32_t)idx * (uint32_t)prm.in_stride_i;
+          const long long tbase = t.in_off + (prm.c2r_sc ? 0 : (long long)col * prm.in_stride_c);
+          const V xk = reinterpret_cast<const V*>(prm.in)[tbase + sidx];
+          const V xm = reinterpret_cast<const V*>(prm.in)[tbase + (prm.c2r_m - sidx)];
+          const T ax = xk.x + xm.x, ay = xk.y - xm.y;
+          const T dx = xk.x - xm.x, dy = xk.y + xm.y;
+          const V wh = __ldg(reinterpret_cast<const V*>(prm.c2r_hi) + (sidx >> prm.c2r_shift));
+          const V wl = __ldg(reinterpret_cast<const V*>(prm.c2r_lo) + (sidx & ((1u << prm.c2r_shift) - 1u)));
+          const cpx<T> w = cmul(cpx<T>(wh.x, wh.y), cpx<T>(wl.x, wl.y));  // W_n^s
+          const T tx = dx * w.x + dy * w.y, ty = dy * w.x - dx * w.y;    // d * conj(w)
+          x[i] = cpx<T>(ax - ty, ay + tx);
+#endif
         } else if (prm.in_real) {
           x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], T(0));
         } else {

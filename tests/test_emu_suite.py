@@ -83,9 +83,9 @@ def test_pending_variants_on_the_emulator():
     GENFFT_TWB_TILED (tile-major inter-pass twiddle table, host and device side).  Their index arithmetic and formulas
     are checked here, the pair operations in their scalar form; the PTX spelling itself only a GPU can check
     (tools/round_start.sh runs the GPU tests against the variant library)."""
-    env = dict(os.environ, GENFFT_TEST_BACKEND="emu", GENFFT_EMU_VARIANT="packed:-DGENFFT_PACKED_F32=1 -DGENFFT_TWB_TILED=1")
+    env = dict(os.environ, GENFFT_TEST_BACKEND="emu", GENFFT_EMU_VARIANT="packed:-DGENFFT_PACKED_F32=1 -DGENFFT_TWB_TILED=1 -DGENFFT_FUSED_C2R=1")
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-n", str(min(8, os.cpu_count() or 1)), "-p", "no:cacheprovider",
-           "-k", "real_fft_vs_reference or r2c_c2r_random", os.path.join(ROOT, "tests", "test_gpu_real_vert_2d.py"),
+           "-k", "real_fft_vs_reference or r2c_c2r_random or half_spectrum_inverse", os.path.join(ROOT, "tests", "test_gpu_real_vert_2d.py"),
            os.path.join(ROOT, "tests", "test_gpu_random_sweep.py")]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-4000:] + r.stderr[-2000:]

@@ -11,3 +11,5 @@ GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed" GENFFT_NVCC_EXTRA="-DGENFFT_PA
 GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed2" GENFFT_NVCC_EXTRA="-DGENFFT_PACKED_F32=2" bash "$ROOT/genfft_b200/csrc/build.sh"
 # packed adds + tile-major inter-pass twiddle table (immediate offsets instead of 15 computed addresses per thread)
 GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_packed_tw" GENFFT_NVCC_EXTRA="-DGENFFT_PACKED_F32=1 -DGENFFT_TWB_TILED=1" bash "$ROOT/genfft_b200/csrc/build.sh"
+# half-spectrum inverse with its pre-process fused into the first pass's load (one pass over HBM less)
+GENFFT_LIB_OUT="$ROOT/genfft_b200/lib_exp_c2r" GENFFT_NVCC_EXTRA="-DGENFFT_FUSED_C2R=1" bash "$ROOT/genfft_b200/csrc/build.sh"

@@ -28,6 +28,13 @@ def r2c(n,batch):
     bytes_=x.numel()*4+y.numel()*8
     print(f"r2c n={n} batch={batch}: best {best:.3f} ms med {med:.3f}  {bytes_/best/1e6:.0f} GB/s {p.describe()}", flush=True)
 
+def c2r(n,batch):
+    x=torch.randn(batch,n//2+1,dtype=torch.complex64,device='cuda'); y=torch.empty(batch,n,device='cuda')
+    p=g.InverseRealFFT(n,np.float32,batch=batch)
+    best,med=time_it(lambda: p.inverse(y,x), iters=10, warm=3)
+    bytes_=x.numel()*8+y.numel()*4
+    print(f"c2r n={n} batch={batch}: best {best:.3f} ms med {med:.3f}  {bytes_/best/1e6:.0f} GB/s {p.describe()}", flush=True)
+
 def fft2d(w,h):
     x=torch.randn(h,w,dtype=torch.complex64,device='cuda'); y=torch.empty_like(x)
     p=g.FFT2D(w,h,np.float32)
@@ -54,6 +61,8 @@ if __name__=="__main__":
         r2c(1<<22, 256)
     if "2d" in which:
         fft2d(4096,4096); fft2d(8192,8192); fft2d(32768,32768)
+    if "c2r" in which:
+        c2r(4096, 1<<16); c2r(1<<22, 64)
     if "r2csmall" in which:
         for n,b in ((4096, 1<<16), (32768, 1<<13)):
             r2c(n,b)

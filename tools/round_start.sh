@@ -13,5 +13,7 @@ nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a tools/tma_tile_bench
 # compile-time variants waiting for an A/B (built beforehand by tools/build_variants.sh; skipped when absent)
 if [ -f genfft_b200/lib_exp_packed/libgenfft_cuda.so ]; then
   python tools/variant_bench.py lib,lib_exp_packed,lib_exp_packed_tw,lib_exp_packed2 c2 c3f c4 c5 > gpurun_out/variant_packed.log 2>&1; cut -c1-120 gpurun_out/variant_packed.log
+  python tools/variant_bench.py lib,lib_exp_c2r c2r > gpurun_out/variant_c2r.log 2>&1; cut -c1-120 gpurun_out/variant_c2r.log
+  GENFFT_CUDA_LIB=$PWD/genfft_b200/lib_exp_c2r/libgenfft_cuda.so python -m pytest tests/test_gpu_real_vert_2d.py tests/test_gpu_random_sweep.py -m gpu -q -x -k 'half_spectrum or r2c_c2r' > gpurun_out/pytest_c2r.log 2>&1; tail -2 gpurun_out/pytest_c2r.log
   GENFFT_CUDA_LIB=$PWD/genfft_b200/lib_exp_packed/libgenfft_cuda.so python -m pytest tests/test_gpu_c2c.py tests/test_gpu_real_vert_2d.py -m gpu -q -x > gpurun_out/pytest_packed.log 2>&1; tail -2 gpurun_out/pytest_packed.log
 fi

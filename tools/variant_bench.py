@@ -29,6 +29,9 @@ for name in libs:
         q.r2c(1 << 22, 256)
     if "c5" in which:
         q.fft2d(32768, 32768)
+    if "c2r" in which:
+        q.c2r(4096, 1 << 16)
+        q.c2r(1 << 22, 64)
     if "c2" in which:
         q.c2c(4096, 1 << 16)
     torch.cuda.empty_cache()

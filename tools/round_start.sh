@@ -17,3 +17,6 @@ if [ -f genfft_b200/lib_exp_packed/libgenfft_cuda.so ]; then
   GENFFT_CUDA_LIB=$PWD/genfft_b200/lib_exp_c2r/libgenfft_cuda.so python -m pytest tests/test_gpu_real_vert_2d.py tests/test_gpu_random_sweep.py -m gpu -q -x -k 'half_spectrum or r2c_c2r' > gpurun_out/pytest_c2r.log 2>&1; tail -2 gpurun_out/pytest_c2r.log
   GENFFT_CUDA_LIB=$PWD/genfft_b200/lib_exp_packed/libgenfft_cuda.so python -m pytest tests/test_gpu_c2c.py tests/test_gpu_real_vert_2d.py -m gpu -q -x > gpurun_out/pytest_packed.log 2>&1; tail -2 gpurun_out/pytest_packed.log
 fi
+# paths written without a GPU at hand (off by default), in a process of their own: a trap there must not poison the rest
+GENFFT_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_chain.py -m gpu -q -k first_two > gpurun_out/pytest_experimental.log 2>&1; tail -2 gpurun_out/pytest_experimental.log
+GENFFT_CUDA_CHAIN12=1 timeout 300 python tools/quick_bench.py c4 > gpurun_out/quick_bench_chain12.log 2>&1; cut -c1-120 gpurun_out/quick_bench_chain12.log

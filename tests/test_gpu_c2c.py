@@ -282,6 +282,8 @@ def test_cached_launch_matches_the_general_driver(dt, n, batch):
     same grid: bit-identical output and one launch each -- forward, inverse, in place, and from an input that is only
     8-byte aligned (no TMA prefetch)."""
     import os
+    if os.environ.get("GENFFT_TEST_BACKEND") == "emu":
+        batch = min(batch, 40)  # the emulator has 3 SMs: 12 tiles already take the TMA-prefetch mode
     tdt = torch.complex64 if dt == np.float32 else torch.complex128
     rng = np.random.default_rng(n + batch)
     x = torch.from_numpy(rand_cpx(rng, batch * n + 1, dt)).cuda()

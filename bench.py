@@ -388,6 +388,12 @@ def extras(g, np, torch) -> dict:
         ms = timed(lambda: (lib.genfft_cuda_exec_c2c_dev(h, py, px, 0, st), lib.genfft_cuda_exec_c2c_dev(h, pz, py, 1, st)),
                    iters=500, warm=50)
         c1["us_per_pair_c_abi_raw_pointers"] = ms * 1e3
+        # the same pair issued from a C loop inside the library (no Python between the launches): what a C/C++ caller of
+        # the device-pointer path pays; host wall-clock over 2000 pairs including the final synchronisation
+        import ctypes
+        us = ctypes.c_double(0.0)
+        if lib.genfft_cuda_debug_time_c2c_pairs(h, pz, py, px, 2000, st, ctypes.byref(us)) == 0:
+            c1["us_per_pair_c_loop"] = us.value
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

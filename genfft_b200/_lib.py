@@ -83,6 +83,7 @@ _SIGNATURES = {
     "genfft_cuda_twiddle2d_dev": (C.c_int, [C.c_int, _vp, _i64, _i64, _i64, _i64, _i64, C.c_int, _vp]),
     "genfft_cuda_transpose_dev": (C.c_int, [C.c_int, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "genfft_cuda_debug_fast_div": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "genfft_cuda_debug_time_c2c_pairs": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.POINTER(C.c_double)]),
     "genfft_cuda_peer_barrier_dev": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint32, _vp]),
     "genfft_cuda_memset_dev": (C.c_int, [_vp, C.c_int, C.c_size_t]),
     "genfft_cuda_malloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),

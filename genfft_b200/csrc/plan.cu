@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1508,6 +1509,27 @@ extern "C" {
 
 int genfft_cuda_exec_c2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, int inverse, void* stream) {
   return exec_c2c_internal(plan, out, in, inverse, (cudaStream_t)stream, false, false, -1, nullptr);
+}
+
+int genfft_cuda_debug_time_c2c_pairs(genfft_cuda_plan_t plan, void* out, void* mid, const void* in, int iters,
+                                     void* stream, double* us_per_pair) {
+  if (!us_per_pair || iters < 1) return fail(GENFFT_CUDA_ERR_ARG, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int warm = 0; warm < 2; warm++) {
+    int rc = exec_c2c_internal(plan, mid, in, 0, st, false, false, -1, nullptr);
+    if (!rc) rc = exec_c2c_internal(plan, out, mid, 1, st, false, false, -1, nullptr);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iters; i++) {
+    int rc = exec_c2c_internal(plan, mid, in, 0, st, false, false, -1, nullptr);
+    if (!rc) rc = exec_c2c_internal(plan, out, mid, 1, st, false, false, -1, nullptr);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  *us_per_pair = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / iters;
+  return GENFFT_CUDA_OK;
 }
 
 int genfft_cuda_exec_c2c_no_scramble_dev(genfft_cuda_plan_t plan, void* inout, int inverse, void* stream) {

@@ -196,6 +196,12 @@ int genfft_cuda_transpose_dev(int precision, void* out, int64_t out_stride, cons
  * x < 2^31); host code only. */
 uint32_t genfft_cuda_debug_fast_div(uint32_t x, uint32_t d);
 
+/* Measurement hook (bench.py, C1): `iters` times forward in -> mid then inverse mid -> out on `stream`, issued from a C
+ * loop and followed by one stream synchronisation; *us_per_pair = host wall-clock per forward+inverse pair, i.e. what
+ * a C/C++ caller of the device-pointer path pays per pair of small transforms (launch-rate bound). */
+int genfft_cuda_debug_time_c2c_pairs(genfft_cuda_plan_t plan, void* out, void* mid, const void* in, int iters,
+                                     void* stream, double* us_per_pair);
+
 /* Stream-ordered barrier across the ranks of one node over IPC-mapped flag arrays: peer_flags[r] is rank r's array
  * of `world` uint32 epochs (zero-initialised with genfft_cuda_memset_dev, mapped with the IPC helpers below); `epoch`
  * must increase by one per barrier.  Replaces a collective-library call between the passes of the distributed 2D

@@ -333,3 +333,19 @@ def test_host_path_leaves_the_gaps_between_transforms_alone(dt):
     g.RealFFT(n, dt, half=True, batch=batch, out_dist=n // 2 + 4).forward(rout, r)
     assert oracle.rel_l2(rout[:, :n // 2 + 1], np.fft.rfft(r.astype(np.float64), axis=1)) <= oracle.tolerance(n, dt)
     assert np.all(rout[:, n // 2 + 1:] == 7.5 - 3.25j)
+
+
+def test_c_loop_pair_timing_hook():
+    """genfft_cuda_debug_time_c2c_pairs (bench.py's C1 figure from a C loop): runs the pairs and leaves the round trip."""
+    import ctypes
+    n = 1024
+    x = torch.from_numpy(rand_cpx(np.random.default_rng(1), n, np.float32)).cuda()
+    y, z = torch.empty_like(x), torch.empty_like(x)
+    plan = g.FFT(n, np.float32)
+    us = ctypes.c_double(0.0)
+    st = torch.cuda.current_stream().cuda_stream
+    n0 = g.launch_count()
+    assert g.lib().genfft_cuda_debug_time_c2c_pairs(plan._h, z.data_ptr(), y.data_ptr(), x.data_ptr(), 20, st, ctypes.byref(us)) == 0
+    torch.cuda.synchronize()
+    assert g.launch_count() - n0 == 2 * (20 + 2) and us.value > 0
+    assert float((z / n - x).abs().max()) < 1e-5

@@ -1,6 +1,7 @@
 #!/bin/bash
 # First GPU call of a round (1 GPU): state of the tree on real hardware in one go.
-#   gpurun --timeout 600 -- bash tools/round_start.sh
+#   bash tools/build_variants.sh                      # HERE first (no GPU, ~4 min): the variant libraries waiting for an A/B
+#   gpurun --timeout 1500 -- bash tools/round_start.sh
 # Writes everything under gpurun_out/ (merged back by gpurun).
 set -u
 mkdir -p gpurun_out

@@ -27,6 +27,7 @@ struct Fiber {
   ucontext_t ctx;
   void* stack = nullptr;
   bool done = true;
+  bool at_barrier = false;  // waiting in __syncthreads(); a fiber that yields while polling (spin_yield) stays runnable
 };
 
 std::mutex g_mu;  // one launch at a time (the globals above are process-wide)
@@ -88,6 +89,13 @@ int num_sms() {
 
 void barrier() {
   g_switches++;
+  g_current->at_barrier = true;
+  swapcontext(&g_current->ctx, &g_main);
+}
+
+// a thread that polls for another thread's action (mbarrier wait) gives the others a turn without arriving at a barrier
+void spin_yield() {
+  g_switches++;
   swapcontext(&g_current->ctx, &g_main);
 }
 
@@ -96,6 +104,10 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thr
   static const bool nolaunch = getenv("GENFFT_EMU_NOLAUNCH") != nullptr;
   if (nolaunch) return;
   std::lock_guard<std::mutex> lk(g_mu);
+  static const int order = [] {
+    const char* o = getenv("GENFFT_EMU_ORDER");
+    return !o ? 0 : !strcmp(o, "reverse") ? 1 : !strcmp(o, "shuffle") ? 2 : 0;
+  }();
   const size_t nthreads = (size_t)block.x * block.y * block.z;
   if (nthreads == 0 || nthreads > 1024 || smem > kSmemBytes) {
     fprintf(stderr, "genfft_emu: bad launch (%zu threads, %zu bytes of shared memory)\n", nthreads, smem);
@@ -125,19 +137,37 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thr
           f.ctx.uc_link = &g_main;
           makecontext(&f.ctx, fiber_entry, 0);
           f.done = false;
+          f.at_barrier = false;
         }
         size_t alive = nthreads;
+        unsigned long long phase = 0;
         while (alive) {
-          for (size_t t = 0; t < nthreads; t++) {
+          // One sweep runs every runnable fiber until it reaches a barrier, polls, or ends.  The barrier opens when
+          // every live fiber waits in it.  Order of the threads within a sweep (GENFFT_EMU_ORDER): forward (default),
+          // reverse, or a different pseudo-random rotation + direction per sweep -- a missing __syncthreads() between
+          // a write and a read shows up as stale data in at least one of them, whichever side has the higher index.
+          phase++;
+          size_t ran = 0;
+          for (size_t slot = 0; slot < nthreads; slot++) {
+            size_t t = slot;
+            if (order == 1) t = nthreads - 1 - slot;
+            else if (order == 2) {
+              const unsigned long long h = (phase * 0x9E3779B97F4A7C15ull) ^ ((unsigned long long)bx * 0xD1B54A32D192ED03ull);
+              const size_t rot = (size_t)((h >> 17) % nthreads);
+              t = (h & 1) ? (rot + slot) % nthreads : (rot + nthreads - slot) % nthreads;
+            }
             Fiber& f = g_fibers[t];
-            if (f.done) continue;
+            if (f.done || f.at_barrier) continue;
             const unsigned tx = (unsigned)(t % block.x), ty = (unsigned)((t / block.x) % block.y),
                            tz = (unsigned)(t / ((size_t)block.x * block.y));
             g_threadIdx = uint3{tx, ty, tz};
             g_current = &f;
             swapcontext(&g_main, &f.ctx);
+            ran++;
             if (f.done) alive--;
           }
+          if (ran == 0)  // every live fiber waits in the barrier: open it
+            for (size_t t = 0; t < nthreads; t++) g_fibers[t].at_barrier = false;
         }
       }
   g_body = nullptr;

@@ -47,6 +47,7 @@ extern dim3 g_blockDim, g_gridDim;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& thread_body);
 unsigned char* dyn_smem();
 void barrier();
+void spin_yield();
 }  // namespace genfft_emu
 #define threadIdx (::genfft_emu::g_threadIdx)
 #define blockIdx (::genfft_emu::g_blockIdx)

@@ -172,3 +172,19 @@ def test_distributed_transforms_real_kernels_over_gloo():
         assert p.exitcode == 0
     res = dict(q.get(timeout=10) for _ in range(world))
     assert len(res) == world and max(res.values()) < 1.0, res  # rel-L2 in units of the tolerance
+
+
+@pytest.mark.parametrize("order", ["reverse", "shuffle"])
+def test_thread_order_independence_on_the_emulator(order):
+    """The emulator runs the threads of a CTA one after another between two barriers; a read that lacks a
+    __syncthreads() after another thread's write sees stale data when the reader runs first.  Forward order (the other
+    tests) exposes that for writers with the higher index, reverse order for the lower, and a different rotation and
+    direction per barrier phase mixes both -- a racecheck for the kernels' shared-memory exchanges without a GPU."""
+    backend.build()
+    env = dict(os.environ, GENFFT_TEST_BACKEND="emu", GENFFT_EMU_ORDER=order)
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-n", str(min(8, os.cpu_count() or 1)), "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_gpu_random_sweep.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 14, r.stdout[-2000:]

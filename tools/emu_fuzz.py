@@ -14,6 +14,7 @@ import genfft_b200 as g
 
 CPX = {np.float32: np.complex64, np.float64: np.complex128}
 TOL = {np.float32: 2e-5, np.float64: 2e-13}
+BIG = int(os.environ.get("GENFFT_FUZZ_BIG", "0"))  # extra bits of size: 3 reaches the three-pass plans (slow)
 SENT = 7.5 - 3.25j
 
 
@@ -31,7 +32,7 @@ def t(x):
 
 
 def case_c2c(rng, dt):
-    n = 1 << int(rng.integers(0, 18)); batch = int(rng.integers(1, max(2, min(64, (1 << 18) // n) + 1)))
+    n = 1 << int(rng.integers(0, 18 + BIG)); batch = int(rng.integers(1, max(2, min(64, (1 << (18 + BIG)) // n) + 1)))
     ind, outd = n + int(rng.integers(0, 4)), n + int(rng.integers(0, 4)); inv = bool(rng.integers(0, 2))
     buf = rc(rng, batch * ind + 2, dt); out = np.full(batch * outd + 2, SENT, CPX[dt])
     off = int(rng.integers(0, 2)) if dt == np.float32 else 0
@@ -51,7 +52,7 @@ def case_c2c(rng, dt):
 
 
 def case_r2c(rng, dt):
-    n = 1 << int(rng.integers(0, 19)); batch = int(rng.integers(1, max(2, min(40, (1 << 18) // n) + 1)))
+    n = 1 << int(rng.integers(0, 19 + BIG)); batch = int(rng.integers(1, max(2, min(40, (1 << (18 + BIG)) // n) + 1)))
     half = bool(rng.integers(0, 2)); lim = 1 if n == 1 else (n // 2 + 1 if half else n)
     outd = lim + int(rng.integers(0, 3)); ind = n + 2 * int(rng.integers(0, 3)) if n >= 2 else n + int(rng.integers(0, 3))
     x = rng.uniform(-1, 1, (batch, ind)).astype(dt); out = np.full((batch, outd), SENT, CPX[dt])

@@ -12,6 +12,11 @@ batch is sharded: every rank transforms its own 2^16 sequences, no collective on
              buffers: H2D + kernels + D2H inside the timed region
   cpu_baseline / --impl reference
              genFFT's own CPU implementation (oracle/_ref, dispatch AVX2/FMA build) on the host cores
+  extras.C5_dist (N > 1 only)
+             BASELINE.json configs[4]: 2D C2C fp32 32768 x 32768 slab-decomposed over the N GPUs with the all-to-all
+             fused into the FFT kernels' stores (genfft_b200.dist.DistFFT2D, transport "p2p"), natural order and
+             transposed output, against the NVLink all-to-all roofline, with a parity figure against genFFT's CPU
+             output taken on the same multi-process path (FFT2D::transform, fft.h:213-241)
 """
 from __future__ import annotations
 
@@ -146,7 +151,10 @@ def reference_arm(args, rank: int, world: int) -> int:
     # a CPU caller writes, and the same host-buffer contract our e2e figure is timed on).
     per_step = min(BATCH * world, 16384)
     t = ref.bench_c2c_array(N_FFT, per_step, threads, args.warmup, args.steps)
-    ms = 1e3 * t
+    # ms_per_step is quoted for the batch the config names (2^16 transforms per GPU); the sweep timed is a bounded
+    # sample of it, scaled by the transform count (the loop is linear in it: independent transforms, DRAM-streaming)
+    sample_ms = 1e3 * t
+    ms = sample_ms * (BATCH * world) / per_step
     value = 5.0 * N_FFT * math.log2(N_FFT) * per_step / t / 1e9
     # the reference's own benchmark loop (fft_bench.cpp FFT_1D: one in/out buffer, fresh input per iteration) keeps
     # the 64 KiB working set in cache; reported beside the streaming figure
@@ -159,7 +167,9 @@ def reference_arm(args, rank: int, world: int) -> int:
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic U(-1,1), std::mt19937_64 per thread", "config": config(args.gpus),
+        "dtype": "f32", "data": "synthetic U(-1,1), std::mt19937_64 per thread",
+        "config": dict(config(args.gpus), reference_sample=sample),
+        "sample_ms_per_step": sample_ms, "sample_transforms_per_step": per_step,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
                          "cache_resident_value": resident,
                          "cache_resident_sample": f"{n_res} transforms through one in/out buffer per thread "
@@ -273,10 +283,13 @@ def main() -> int:
     peak, peak_src = measured_peaks()
     kernel_ms = sum(per_kernel_ms) / len(per_kernel_ms)
     achieved = ALGO_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "c2_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_source = ("constant read from profiles/c2_traffic.json (one `ncu --set full` capture of this kernel, "
+                          f"{tj.get('source', 'see profiles/')}); NOT measured by this run")
     except Exception:
         pass
     line = {
@@ -288,7 +301,7 @@ def main() -> int:
                 "d2h_bytes_per_step": N_FFT * BATCH * 8, "ms_per_step": e2e_s * 1e3,
                 "api": "genfft_cuda_exec_c2c (host pointers, pinned; chunked H2D/compute/D2H overlap on two streams)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fft_tile_kernel<float,4096,16,1,M_ROWTMA,false> (cp.async.bulk prefetch)",
+                     "traffic": traffic, "traffic_source": traffic_source, "kernel": "fft_tile_kernel<float,4096,16,1,M_ROWTMA,false> (cp.async.bulk prefetch)",
                      "kernel_ms": kernel_ms, "algorithmic_bytes": ALGO_BYTES_PER_STEP, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "plan": plan.describe(),

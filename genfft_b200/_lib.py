@@ -57,6 +57,7 @@ _SIGNATURES = {
     "genfft_cuda_exec_r2c_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "genfft_cuda_exec_c2c_interleave_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "genfft_cuda_separate_2x_real_dev": (C.c_int, [C.c_int, _vp, _vp, _vp, _i64, _vp]),
+    "genfft_cuda_separate_2x_real": (C.c_int, [C.c_int, _vp, _vp, _vp, _i64]),
     "genfft_cuda_plan_r2c_2d": (C.c_int, [_plan_p, C.c_int, _i64, _i64]),
     "genfft_cuda_exec_r2c_2d_dev": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "genfft_cuda_exec_c2c_interleave": (C.c_int, [_vp, _vp, _vp, _vp]),

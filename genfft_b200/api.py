@@ -211,13 +211,19 @@ class FFT(_Plan):
 
 
 def separate_2x_real_FFT(out1, out2, inp, n: int):
-    """genfft::separate_2x_real_FFT(out1, out2, in, N) (FFTReal.h:35-66) on device tensors; out1/out2 may alias in."""
+    """genfft::separate_2x_real_FFT(out1, out2, in, N) (FFTReal.h:35-66); device tensors or host arrays (all three on
+    the same side); out1/out2 may alias in."""
     o1, o2, i = _Buf(out1, True), _Buf(out2, True), _Buf(inp)
-    if not (o1.cuda and o2.cuda and i.cuda):
-        raise ValueError("separate_2x_real_FFT works on device tensors (use the C++ mirror's host version otherwise)")
+    if not (o1.cuda == o2.cuda == i.cuda):
+        raise ValueError("separate_2x_real_FFT: the three buffers must all be device tensors or all host arrays")
+    if not (o1.precision == o2.precision == i.precision):
+        raise TypeError("separate_2x_real_FFT: buffers of different precision")
     if min(o1.nscalars, o2.nscalars, i.nscalars) < 2 * n:
         raise ValueError("buffers must hold n complex elements")
-    check(lib().genfft_cuda_separate_2x_real_dev(i.precision, o1.ptr, o2.ptr, i.ptr, n, _stream()))
+    if i.cuda:
+        check(lib().genfft_cuda_separate_2x_real_dev(i.precision, o1.ptr, o2.ptr, i.ptr, n, _stream()))
+    else:
+        check(lib().genfft_cuda_separate_2x_real(i.precision, o1.ptr, o2.ptr, i.ptr, n))
     return out1, out2
 
 
@@ -317,6 +323,8 @@ class FFTVert(_Plan):
         b = _Buf(data, True)
         if b.precision != self.precision:
             raise TypeError("buffer dtype does not match the plan's precision")
+        if self._n and cols and b.nscalars < 2 * ((self._n - 1) * stride + cols):
+            raise ValueError("buffer too small for n x cols with the given stride")
         if b.cuda:
             check(lib().genfft_cuda_exec_vert_no_scramble_dev(self._h, b.ptr, stride, cols, int(inv), _stream()))
         else:
@@ -339,6 +347,9 @@ class DIT(_Plan):
         """DIT<T>::apply(out, in, half) (fft.h:181-189); out may alias in."""
         self._need()
         o, i = _pair(out, inp, self.precision)
+        n = self._n
+        if i.nscalars < 2 * max(1, n // 2) or o.nscalars < 2 * (1 if n <= 1 else (n // 2 + 1 if half else n)):
+            raise ValueError("buffer too small: DIT::apply reads n/2 complex elements and writes n/2+1 (half) or n")
         if o.cuda:
             check(lib().genfft_cuda_exec_dit_dev(self._h, o.ptr, i.ptr, int(half), _stream()))
         else:

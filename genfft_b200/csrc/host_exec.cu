@@ -105,6 +105,7 @@ extern "C" {
 int genfft_cuda_exec_c2c(genfft_cuda_plan_t plan, void* out, const void* in, int inverse) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in) return set_error(GENFFT_CUDA_ERR_ARG, "FFT::transform requires out != in");
   const size_t es = elem_size(p->precision);
@@ -114,6 +115,7 @@ int genfft_cuda_exec_c2c(genfft_cuda_plan_t plan, void* out, const void* in, int
 int genfft_cuda_exec_c2c_no_scramble(genfft_cuda_plan_t plan, void* inout, int inverse) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!inout) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (p->in_dist != p->out_dist) return set_error(GENFFT_CUDA_ERR_ARG, "in-place transform needs in_dist == out_dist");
   const size_t es = elem_size(p->precision);
@@ -123,6 +125,7 @@ int genfft_cuda_exec_c2c_no_scramble(genfft_cuda_plan_t plan, void* inout, int i
 int genfft_cuda_exec_c2c_real_in(genfft_cuda_plan_t plan, void* out, const void* in_real) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in_real) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   const size_t es = elem_size(p->precision);
   return exec_batched_host(p, out, in_real, es / 2, p->in_dist, p->n, es, p->out_dist, p->n, false, 0, false, true);
@@ -132,6 +135,7 @@ int genfft_cuda_exec_c2c_real_in(genfft_cuda_plan_t plan, void* out, const void*
 int genfft_cuda_exec_c2c_interleave(genfft_cuda_plan_t plan, void* out, const void* in1, const void* in2) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in1 || !in2) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (p->batch != 1) return set_error(GENFFT_CUDA_ERR_ARG, "transform_interleave on host pointers supports batch 1");
   const size_t es = elem_size(p->precision);
@@ -154,6 +158,7 @@ int genfft_cuda_exec_c2c_interleave(genfft_cuda_plan_t plan, void* out, const vo
 int genfft_cuda_exec_r2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stride, const void* in, int64_t in_stride) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_2D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out_stride < p->width || in_stride < p->width) return set_error(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
   const size_t es = elem_size(p->precision);
@@ -177,6 +182,7 @@ int genfft_cuda_exec_r2c_2d_2x(genfft_cuda_plan_t plan, void* out, int64_t out_s
                                int64_t in_stride1, const void* in2, int64_t in_stride2) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_2D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in1 || !in2) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out_stride < p->width || in_stride1 < p->width || in_stride2 < p->width)
     return set_error(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
@@ -203,17 +209,23 @@ int genfft_cuda_exec_r2c_2d_2x(genfft_cuda_plan_t plan, void* out, int64_t out_s
 int genfft_cuda_exec_c2r(genfft_cuda_plan_t plan, void* out, const void* in) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2R_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2r_1d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   const size_t es = elem_size(p->precision);
   const size_t in_bytes = ((size_t)(p->batch - 1) * p->in_dist + p->n / 2 + 1) * es;
-  const size_t out_bytes = ((size_t)(p->batch - 1) * p->out_dist + p->n) * es / 2;
+  const size_t out_row = (size_t)p->out_dist * es / 2, out_last = (size_t)p->n * es / 2;
+  const size_t out_bytes = (size_t)(p->batch - 1) * out_row + out_last;
   int rc = ensure_stage(p, in_bytes, out_bytes);
   if (rc) return rc;
   cudaStream_t st = p->streams[0];
   HX_TRY(cudaMemcpyAsync(p->stage_in, in, in_bytes, cudaMemcpyHostToDevice, st));
   rc = genfft_cuda_exec_c2r_dev(plan, p->stage_out, p->stage_in, st);
   if (rc) return rc;
-  HX_TRY(cudaMemcpyAsync(out, p->stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  // only the transforms themselves come back: the caller's memory between two outputs (out_dist > n) is not ours to write
+  if (out_row == out_last || p->batch == 1)
+    HX_TRY(cudaMemcpyAsync(out, p->stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  else
+    HX_TRY(cudaMemcpy2DAsync(out, out_row, p->stage_out, out_row, out_last, (size_t)p->batch, cudaMemcpyDeviceToHost, st));
   HX_TRY(cudaStreamSynchronize(st));
   return GENFFT_CUDA_OK;
 }
@@ -221,6 +233,7 @@ int genfft_cuda_exec_c2r(genfft_cuda_plan_t plan, void* out, const void* in) {
 int genfft_cuda_exec_r2c(genfft_cuda_plan_t plan, void* out, const void* in) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_1D) return set_error(GENFFT_CUDA_ERR_ARG, "not an r2c_1d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   const size_t es = elem_size(p->precision);
   const long long out_len = p->n == 1 ? 1 : (p->half ? p->n / 2 + 1 : p->n);
@@ -231,6 +244,7 @@ int genfft_cuda_exec_c2c_2d(genfft_cuda_plan_t plan, void* out, int64_t out_stri
                             int inverse) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2C_2D) return set_error(GENFFT_CUDA_ERR_ARG, "not a c2c_2d plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in) return set_error(GENFFT_CUDA_ERR_ARG, "FFT2D::transform requires out != in");
   if (out_stride < p->width || in_stride < p->width) return set_error(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
@@ -251,6 +265,7 @@ int genfft_cuda_exec_vert(genfft_cuda_plan_t plan, void* out, int64_t out_stride
                           int64_t cols, int inverse) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_VERT) return set_error(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in) return set_error(GENFFT_CUDA_ERR_ARG, "FFTVert::transform requires out != in");
   if (cols < 0 || out_stride < cols || in_stride < cols) return set_error(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
@@ -271,6 +286,7 @@ int genfft_cuda_exec_vert(genfft_cuda_plan_t plan, void* out, int64_t out_stride
 int genfft_cuda_exec_vert_no_scramble(genfft_cuda_plan_t plan, void* data, int64_t stride, int64_t cols, int inverse) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_VERT) return set_error(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!data) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (cols < 0 || stride < cols) return set_error(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
   if (cols == 0) return GENFFT_CUDA_OK;
@@ -287,9 +303,33 @@ int genfft_cuda_exec_vert_no_scramble(genfft_cuda_plan_t plan, void* data, int64
   return GENFFT_CUDA_OK;
 }
 
+// separate_2x_real_FFT(out1, out2, in, N) (include/genFFT/FFTReal.h:35-66) on host pointers.  No plan exists for it
+// (the reference's is a free function), so the staging is per call; out1 or out2 may alias in, as in the reference.
+int genfft_cuda_separate_2x_real(int precision, void* out1, void* out2, const void* in, int64_t n) {
+  if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return set_error(GENFFT_CUDA_ERR_ARG, "bad precision");
+  if (!out1 || !out2 || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (n < 1 || n > (1LL << 27)) return set_error(GENFFT_CUDA_ERR_SIZE, "unsupported size");
+  const size_t bytes = (size_t)n * elem_size(precision);
+  const size_t slot = (bytes + 255) & ~(size_t)255;
+  char* d = nullptr;
+  if (cudaMalloc(&d, 3 * slot) != cudaSuccess) return set_error(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc of staging failed");
+  int rc = GENFFT_CUDA_OK;
+  cudaError_t e = cudaMemcpy(d, in, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = genfft_cuda_separate_2x_real_dev(precision, d + slot, d + 2 * slot, d, n, nullptr);
+    if (!rc) e = cudaMemcpy(out1, d + slot, bytes, cudaMemcpyDeviceToHost);
+    if (!rc && e == cudaSuccess) e = cudaMemcpy(out2, d + 2 * slot, bytes, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_error(GENFFT_CUDA_ERR_CUDA, cudaGetErrorString(e));
+  return GENFFT_CUDA_OK;
+}
+
 int genfft_cuda_exec_dit(genfft_cuda_plan_t plan, void* out, const void* in, int half) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_DIT) return set_error(GENFFT_CUDA_ERR_ARG, "not a dit plan");
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
   if (!out || !in) return set_error(GENFFT_CUDA_ERR_ARG, "null buffer");
   const size_t es = elem_size(p->precision);
   const long long n = p->n;

@@ -671,20 +671,24 @@ static void build_fast_path(Plan* p) {
 // One launch for two consecutive passes with the intermediate kept in L2 (chain_kernel.cuh).
 static int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaStream_t stream) {
   const size_t need = 1 + (size_t)cp.ngroups;
+  void* ctr = nullptr;
   {
+    // one counter block per stream: two executions of the plan on different streams may run at the same time
     std::lock_guard<std::mutex> lk(plan->mu);
-    if (plan->chain_ctr_count < need) {
-      if (plan->chain_ctr) {
-        CU_TRY(cudaDeviceSynchronize());
-        CU_TRY(cudaFree(plan->chain_ctr));
-        plan->chain_ctr = nullptr;
-        plan->chain_ctr_count = 0;
+    Plan::ChainCtr& cc = plan->chain_ctrs[stream];
+    if (cc.count < need) {
+      if (cc.ptr) {
+        CU_TRY(cudaStreamSynchronize(stream));  // earlier launches on this stream are the block's only users
+        CU_TRY(cudaFree(cc.ptr));
+        cc.ptr = nullptr;
+        cc.count = 0;
       }
       const size_t cap = std::max<size_t>(need, 4096);
-      if (cudaMalloc(&plan->chain_ctr, cap * sizeof(uint32_t)) != cudaSuccess)
+      if (cudaMalloc(&cc.ptr, cap * sizeof(uint32_t)) != cudaSuccess)
         return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc of %zu chain counters failed", cap);
-      plan->chain_ctr_count = cap;
+      cc.count = cap;
     }
+    ctr = cc.ptr;
   }
   int occ = 0;
   {
@@ -712,8 +716,8 @@ static int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaS
     cp.lag = std::max(cp.lag, 2u);
   }
   cp.lag = std::min(cp.lag, cp.ngroups);
-  cp.ctr = static_cast<uint32_t*>(plan->chain_ctr);
-  CU_TRY(cudaMemsetAsync(plan->chain_ctr, 0, need * sizeof(uint32_t), stream));
+  cp.ctr = static_cast<uint32_t*>(ctr);
+  CU_TRY(cudaMemsetAsync(ctr, 0, need * sizeof(uint32_t), stream));
   ce->launch(cp, (unsigned)std::min(total, resident), stream);
   g_launches++;
   CU_TRY(cudaGetLastError());
@@ -1185,6 +1189,14 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
 // ------------------------------------------------------------------------------------------------
 // plan creation
 // ------------------------------------------------------------------------------------------------
+// A plan's tables, scratch and launch attributes live on the device it was created on.
+static int enter_exec(const Plan* p) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != p->device)
+    return fail(GENFFT_CUDA_ERR_ARG, "plan was created on device %d but device %d is current", p->device, dev);
+  return GENFFT_CUDA_OK;
+}
+
 static int new_plan(Plan** out, PlanKind kind, int precision) {
   if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return fail(GENFFT_CUDA_ERR_ARG, "bad precision %d", precision);
   int dev, sms;
@@ -1200,6 +1212,21 @@ static int new_plan(Plan** out, PlanKind kind, int precision) {
 }
 
 static const long long kMaxN = 1LL << 27;
+// Tile counts are 32-bit and the smallest tile holds 256 points; column / batch counts are ints.  2^38 points is
+// 2 TiB in single precision, far beyond the device's memory, so this only rejects nonsense before it wraps.
+static const long long kMaxPoints = 1LL << 38;
+static int check_volume(long long n, long long batch) {
+  if (batch > 0x7fffff00LL || n * batch > kMaxPoints)
+    return fail(GENFFT_CUDA_ERR_SIZE, "batch %lld x %lld points exceeds the supported volume", batch, n);
+  return GENFFT_CUDA_OK;
+}
+// consecutive transforms of a batch must not overlap: distances below the transform's extent (or negative) would
+// give overlapping or out-of-bounds stores
+static int check_dist(long long batch, long long dist, long long extent, const char* what) {
+  if (dist < 0 || (batch > 1 && dist < extent))
+    return fail(GENFFT_CUDA_ERR_ARG, "%s = %lld is smaller than the %lld elements of one transform", what, dist, extent);
+  return GENFFT_CUDA_OK;
+}
 
 // sequence + twiddles of an n-point real transform (n/2-point packed complex transform + split)
 static int setup_r2c_tables(Plan* p, int precision, long long n) {
@@ -1250,8 +1277,12 @@ int genfft_cuda_plan_c2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
   if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
   if (!is_pow2(n) || n > kMaxN) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld (power of two <= 2^27 required)", (long long)n);
   if (batch < 1) return fail(GENFFT_CUDA_ERR_ARG, "batch must be >= 1");
+  int rc = check_volume(n, batch);
+  if (!rc) rc = check_dist(batch, in_dist ? in_dist : n, n, "in_dist");
+  if (!rc) rc = check_dist(batch, out_dist ? out_dist : n, n, "out_dist");
+  if (rc) return rc;
   Plan* p;
-  int rc = new_plan(&p, PLAN_C2C_1D, precision);
+  rc = new_plan(&p, PLAN_C2C_1D, precision);
   if (rc) return rc;
   p->n = n;
   p->batch = batch;
@@ -1272,8 +1303,12 @@ int genfft_cuda_plan_r2c_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
   if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
   if (!is_pow2(n) || n > 2 * kMaxN) return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld", (long long)n);
   if (batch < 1) return fail(GENFFT_CUDA_ERR_ARG, "batch must be >= 1");
+  int rc = check_volume(n, batch);
+  if (!rc) rc = check_dist(batch, in_dist ? in_dist : n, n, "in_dist");
+  if (!rc) rc = check_dist(batch, out_dist ? out_dist : (half ? n / 2 + 1 : n), n == 1 ? 1 : (half ? n / 2 + 1 : n), "out_dist");
+  if (rc) return rc;
   Plan* p;
-  int rc = new_plan(&p, PLAN_R2C_1D, precision);
+  rc = new_plan(&p, PLAN_R2C_1D, precision);
   if (rc) return rc;
   p->n = n;
   p->batch = batch;
@@ -1297,8 +1332,10 @@ int genfft_cuda_plan_c2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t wid
   if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
   if (!is_pow2(width) || !is_pow2(height) || width > kMaxN || height > kMaxN)
     return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld x %lld", (long long)width, (long long)height);
+  int rc = check_volume(width, height);
+  if (rc) return rc;
   Plan* p;
-  int rc = new_plan(&p, PLAN_C2C_2D, precision);
+  rc = new_plan(&p, PLAN_C2C_2D, precision);
   if (rc) return rc;
   p->width = width;
   p->height = height;
@@ -1363,7 +1400,8 @@ int genfft_cuda_plan_destroy(genfft_cuda_plan_t plan) {
   if (!plan) return GENFFT_CUDA_OK;
   Plan* p = plan;
   if (p->scratch) cudaFree(p->scratch);
-  if (p->chain_ctr) cudaFree(p->chain_ctr);
+  for (auto& kv : p->chain_ctrs)
+    if (kv.second.ptr) cudaFree(kv.second.ptr);
   if (p->aux) cudaFree(p->aux);
   if (p->stage_in) cudaFree(p->stage_in);
   if (p->stage_out) cudaFree(p->stage_out);
@@ -1421,6 +1459,7 @@ int exec_c2c_internal(Plan* p, void* out, const void* in, int inverse, cudaStrea
                       long long batch, const void* in2) {
   KnobScope knob_scope;
   if (!p || p->kind != PLAN_C2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (batch < 0) batch = p->batch;
   if (p->seq.passes.empty()) {  // n == 1: the transform is the identity
@@ -1465,6 +1504,7 @@ int exec_r2c_strided(Plan* pl, void* out, const void* in, cudaStream_t st, long 
                      long long out_dist_o) {
   KnobScope knob_scope;
   if (!pl || (pl->kind != PLAN_R2C_1D && pl->kind != PLAN_R2C_2D)) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c plan");
+  if (int rc_dev = enter_exec(pl)) return rc_dev;
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (batch < 0) batch = pl->batch;
   Plan* p = pl;
@@ -1545,6 +1585,7 @@ int genfft_cuda_exec_c2c_interleave_dev(genfft_cuda_plan_t plan, void* out, cons
                                         void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2C_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_1d plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in1 || !in2) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in1 || out == in2) return fail(GENFFT_CUDA_ERR_ARG, "transform_interleave requires out != in");
   return exec_c2c_internal(p, out, in1, 0, (cudaStream_t)stream, false, true, -1, in2);
@@ -1588,8 +1629,10 @@ int genfft_cuda_plan_r2c_2d(genfft_cuda_plan_t* plan, int precision, int64_t wid
   if (!plan) return fail(GENFFT_CUDA_ERR_ARG, "plan is null");
   if (!is_pow2(width) || !is_pow2(height) || width > kMaxN || height > kMaxN || width < 2)
     return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld x %lld", (long long)width, (long long)height);
+  int rc = check_volume(width, height);
+  if (rc) return rc;
   Plan* p;
-  int rc = new_plan(&p, PLAN_R2C_2D, precision);
+  rc = new_plan(&p, PLAN_R2C_2D, precision);
   if (rc) return rc;
   p->width = width;
   p->height = height;
@@ -1616,6 +1659,7 @@ int genfft_cuda_exec_r2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_
                                 int64_t in_stride, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_2D) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "RealFFT2D::forward requires out != in");
   if (out_stride < p->width || in_stride < p->width) return fail(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
@@ -1659,6 +1703,7 @@ int genfft_cuda_exec_r2c_2d_2x_dev(genfft_cuda_plan_t plan, void* out, int64_t o
   KnobScope knob_scope;
   Plan* p = plan;
   if (!p || p->kind != PLAN_R2C_2D) return fail(GENFFT_CUDA_ERR_ARG, "not an r2c_2d plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in1 || !in2) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in1 || out == in2) return fail(GENFFT_CUDA_ERR_ARG, "RealFFT2D::forward_2x requires out != in");
   if (out_stride < p->width || in_stride1 < p->width || in_stride2 < p->width)
@@ -1700,8 +1745,12 @@ int genfft_cuda_plan_c2r_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
   if (!is_pow2(n) || n < 2 || n > 2 * kMaxN)
     return fail(GENFFT_CUDA_ERR_SIZE, "unsupported size %lld (power of two >= 2 required)", (long long)n);
   if (batch < 1) return fail(GENFFT_CUDA_ERR_ARG, "batch must be >= 1");
+  int rc = check_volume(n, batch);
+  if (!rc) rc = check_dist(batch, in_dist ? in_dist : n / 2 + 1, n / 2 + 1, "in_dist");
+  if (!rc) rc = check_dist(batch, out_dist ? out_dist : n, n, "out_dist");
+  if (rc) return rc;
   Plan* p;
-  int rc = new_plan(&p, PLAN_C2R_1D, precision);
+  rc = new_plan(&p, PLAN_C2R_1D, precision);
   if (rc) return rc;
   p->n = n;
   p->batch = batch;
@@ -1726,6 +1775,7 @@ int genfft_cuda_plan_c2r_1d(genfft_cuda_plan_t* plan, int precision, int64_t n, 
 int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2R_1D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2r_1d plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "c2r requires out != in");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1790,6 +1840,7 @@ int genfft_cuda_exec_c2c_2d_dev(genfft_cuda_plan_t plan, void* out, int64_t out_
                                 int64_t in_stride, int inverse, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_C2C_2D) return fail(GENFFT_CUDA_ERR_ARG, "not a c2c_2d plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "FFT2D::transform requires out != in (fft.h:209)");
   if (out_stride < p->width || in_stride < p->width) return fail(GENFFT_CUDA_ERR_ARG, "stride smaller than width");
@@ -1818,6 +1869,7 @@ int genfft_cuda_exec_vert_dev(genfft_cuda_plan_t plan, void* out, int64_t out_st
                               int64_t in_stride, int64_t cols, int inverse, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_VERT) return fail(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (out == in) return fail(GENFFT_CUDA_ERR_ARG, "FFTVert::transform requires out != in (fft.h:141)");
   if (cols < 0 || out_stride < cols || in_stride < cols) return fail(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
@@ -1842,6 +1894,7 @@ int genfft_cuda_exec_vert_no_scramble_dev(genfft_cuda_plan_t plan, void* data, i
                                           int inverse, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_VERT) return fail(GENFFT_CUDA_ERR_ARG, "not a vert plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!data) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   if (cols < 0 || stride < cols) return fail(GENFFT_CUDA_ERR_ARG, "bad cols/stride");
   if (cols == 0 || p->seq.passes.empty()) return GENFFT_CUDA_OK;
@@ -1854,6 +1907,7 @@ int genfft_cuda_exec_vert_no_scramble_dev(genfft_cuda_plan_t plan, void* data, i
 int genfft_cuda_exec_dit_dev(genfft_cuda_plan_t plan, void* out, const void* in, int half, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_DIT) return fail(GENFFT_CUDA_ERR_ARG, "not a dit plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!out || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   return launch_dit(p, out, 0, in, 0, (int)p->n, half != 0, 1, false, (cudaStream_t)stream);
 }
@@ -1892,6 +1946,7 @@ int genfft_cuda_exec_dist_rows_dev(genfft_cuda_plan_t plan, void* out, void* con
                                    int64_t row0, const void* in, int64_t in_stride, int inverse, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_DIST_ROWS) return fail(GENFFT_CUDA_ERR_ARG, "not a dist_rows plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!in || (!out && !out_peers)) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   const long long Wp = p->width / p->nparts;
   const size_t es = elem_size(p->precision);
@@ -1934,6 +1989,7 @@ int genfft_cuda_exec_dist_cols_dev(genfft_cuda_plan_t plan, void* out, void* con
                                    int64_t col0, void* data, int64_t stride, int inverse, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_DIST_COLS) return fail(GENFFT_CUDA_ERR_ARG, "not a dist_cols plan");
+  if (int rc_dev = enter_exec(p)) return rc_dev;
   if (!data || (!out && !out_peers)) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
   std::vector<Step> steps;
   seq_steps(p->seq, true, steps, false, false);

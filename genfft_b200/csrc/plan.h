@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -69,14 +70,20 @@ struct Plan {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   size_t scratch_need = 0;  // upper bound known at plan time (0 if none / depends on exec args)
-  void* chain_ctr = nullptr;  // ticket + per-group counters of the L2-resident pass chains (chain_kernel.cuh)
-  size_t chain_ctr_count = 0;
+  // ticket + per-group counters of the L2-resident pass chains (chain_kernel.cuh), one block PER STREAM: launches on
+  // one stream are ordered, launches of the same plan on different streams may overlap and must not share counters
+  struct ChainCtr {
+    void* ptr = nullptr;
+    size_t count = 0;
+  };
+  std::map<cudaStream_t, ChainCtr> chain_ctrs;
   void* aux = nullptr;  // device staging owned by device-pointer entry points (c2r pre-processed spectrum)
   size_t aux_bytes = 0;
   // host-pointer staging
   void* stage_in = nullptr;
   void* stage_out = nullptr;
   size_t stage_in_bytes = 0, stage_out_bytes = 0;
+  std::mutex host_mu;  // host-pointer entry points hold it for the whole call (staging buffers, streams)
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t events[8] = {};
   bool streams_ready = false;

@@ -52,8 +52,13 @@ uint64_t genfft_cuda_launch_count(void);
 /* ---- plans --------------------------------------------------------------------------------------
  * A plan is immutable after creation and may be executed concurrently from several host threads on
  * different streams as long as the executions do not share the plan's internal scratch (plans that
- * need scratch serialise on the stream they are given).  Plans are created on the current CUDA
- * device.  Replaces FFT<T>::FFT(int n) -> factory(n, T()) (include/genFFT/fft.h:59-64). */
+ * need scratch serialise on the stream they are given; the counters of the L2-resident pass chains
+ * are kept per stream).  Plans are created on the current CUDA device and must be executed with that
+ * device current (GENFFT_CUDA_ERR_ARG otherwise).  The HOST-pointer entry points share one set of
+ * staging buffers per plan and therefore serialise per plan (an internal mutex is held for the whole
+ * call): concurrent host-pointer calls on one plan are safe but do not overlap -- use one plan per
+ * thread for that.  Batched plans reject distances smaller than one transform (GENFFT_CUDA_ERR_ARG).
+ * Replaces FFT<T>::FFT(int n) -> factory(n, T()) (include/genFFT/fft.h:59-64). */
 
 /* 1D complex, n points, `batch` transforms; in_dist/out_dist between consecutive transforms
  * (0 = n).  FFT<T> (fft.h:54-113). */
@@ -152,6 +157,8 @@ int genfft_cuda_exec_vert(genfft_cuda_plan_t plan, void* out, int64_t out_stride
 int genfft_cuda_exec_vert_no_scramble(genfft_cuda_plan_t plan, void* data, int64_t stride, int64_t cols,
                                       int inverse);
 int genfft_cuda_exec_dit(genfft_cuda_plan_t plan, void* out, const void* in, int half);
+/* separate_2x_real_FFT(out1, out2, in, N) (FFTReal.h:35-66) on host pointers; out1 or out2 may alias in. */
+int genfft_cuda_separate_2x_real(int precision, void* out1, void* out2, const void* in, int64_t n);
 
 /* ---- distributed 2D building blocks (slab decomposition; one process per GPU) ---------------------------
  * The host side (genfft_b200/dist.py) owns the process group; these run the local passes.

@@ -220,23 +220,16 @@ class FFT2D {
 };
 
 ///@brief Recovers two transforms of real data from one interleaved transform (FFTReal.h:35-66).
-/// Pure index arithmetic on the host, restated from the formulae: X = (Z[i] + conj Z[N-i]) / 2,
-/// Y = (Z[i] - conj Z[N-i]) / (2i).  Input and outputs may alias as in the reference.
+/// Host pointers; runs on the device through the C ABI like everything else (no CPU arithmetic in this header).
+/// Input and outputs may alias as in the reference.
 template <class T>
 void separate_2x_real_FFT(std::complex<T>* out1, std::complex<T>* out2, const std::complex<T>* in, int N) {
-  const std::complex<T> z0 = in[0];
-  out1[0] = std::complex<T>(z0.real(), 0);
-  out2[0] = std::complex<T>(z0.imag(), 0);
-  for (int i = 1; i <= N / 2; i++) {
-    const int k = N - i;
-    const std::complex<T> a = in[i], b = in[k];
-    const T xr = (a.real() + b.real()) * T(0.5), xi = (a.imag() - b.imag()) * T(0.5);
-    const T yr = (b.imag() + a.imag()) * T(0.5), yi = (b.real() - a.real()) * T(0.5);
-    out1[i] = std::complex<T>(xr, xi);
-    out2[i] = std::complex<T>(yr, yi);
-    out1[k] = std::complex<T>(xr, -xi);
-    out2[k] = std::complex<T>(yr, -yi);
-  }
+  detail::check(genfft_cuda_separate_2x_real(detail::precision_of<T>::value, out1, out2, in, N));
+}
+///@brief the same on device pointers
+template <class T>
+void separate_2x_real_FFT_dev(void* d_out1, void* d_out2, const void* d_in, int N, void* stream = nullptr) {
+  detail::check(genfft_cuda_separate_2x_real_dev(detail::precision_of<T>::value, d_out1, d_out2, d_in, N, stream));
 }
 
 ///@brief 2D FFT of a real image (mirror of genfft::RealFFT2D<T>, FFTReal.h:71-184); forward only, as in the reference

@@ -216,6 +216,17 @@ class Ref(_Lib):
             return out
         return super().c2c(x, inverse)
 
+    def c2c_rows(self, x: np.ndarray, inverse: bool = False, threads: int = 0) -> np.ndarray:
+        """FFT<T>::transform on every row of a 2-D host array, one plan, `threads` workers (0 = all host threads)."""
+        x = np.ascontiguousarray(x)
+        count, n = x.shape
+        out = np.empty_like(x)
+        f = self._fn("c2c_rows", _real_dtype(x),
+                     argtypes=[_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_long, _c.c_int, _c.c_int])
+        if f(_ptr(out), _ptr(x), n, count, threads or self.hardware_threads(), int(inverse)):
+            raise ValueError(f"c2c_rows rejected n={n}")
+        return out
+
     def dummy_complex(self, n: int, dtype=np.float32, real: bool = False) -> np.ndarray:
         """DummyData(std::vector<std::complex<T>>&, real) -- test/test_util.h:36-47."""
         out = np.empty(n, dtype=_CPX[np.dtype(dtype)])

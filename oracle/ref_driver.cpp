@@ -182,6 +182,25 @@ double timed_parallel(long count, int threads, Body body) {
 
 }  // namespace
 
+// `count` independent length-n transforms of a host array (rows `n` apart), each thread looping
+// FFT<T>::transform (fft.h:80-85) over its share with one plan held alive -- the comparand of the full-size
+// 2D parity tests (the row pass of FFT2D::scramble_row_fft, fft.h:229-241, is exactly this loop).
+template <class T>
+static int c2c_rows(T *out, const T *in, int n, long count, int threads, int inverse) {
+  if (!valid_pow2(n) || out == in || count < 0) return 1;
+  genfft::FFT<T> keep_plan(n);
+  timed_parallel<T>(count, threads, [&](int, long lo, long hi) {
+    genfft::FFT<T> fft(n);
+    for (long k = lo; k < hi; k++) {
+      if (inverse)
+        fft.template transform<true>((cpx<T> *)out + (size_t)k * n, (const cpx<T> *)in + (size_t)k * n);
+      else
+        fft.template transform<false>((cpx<T> *)out + (size_t)k * n, (const cpx<T> *)in + (size_t)k * n);
+    }
+    return 0.0;
+  });
+  return 0;
+}
 extern "C" {
 
 const char *genfft_ref_describe() {
@@ -425,6 +444,13 @@ double genfft_ref_bench_fft2d_f32(int w, int h, long count) {
     acc += now_s() - t0;
   }
   return acc;
+}
+
+int genfft_ref_c2c_rows_f32(float *out, const float *in, int n, long count, int threads, int inv) {
+  return c2c_rows<float>(out, in, n, count, threads, inv);
+}
+int genfft_ref_c2c_rows_f64(double *out, const double *in, int n, long count, int threads, int inv) {
+  return c2c_rows<double>(out, in, n, count, threads, inv);
 }
 
 int genfft_ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }

@@ -1,5 +1,6 @@
 """Worker for tests/test_gpu_dist.py (launched with torch.distributed.run, one rank per GPU):
-slab-decomposed 2D FFT on small arrays, both transports, against numpy's fft2 of the full array."""
+slab-decomposed 2D FFT and four-step 1D FFT on small arrays, both transports, against genFFT's CPU output of the
+full array (oracle.Ref: FFT2D::transform, fft.h:213-241 / FFT::transform, fft.h:80-85)."""
 import os
 import sys
 
@@ -9,7 +10,26 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import oracle  # noqa: E402  (tests may use the checker)
 from genfft_b200.dist import DistFFT1D, DistFFT2D, four_step_shape  # noqa: E402
+
+# the parity target is genFFT's own CPU output (the compiled reference travels to the GPU box as oracle/_ref);
+# numpy (verified against it in the survey) stands in only when that build is absent
+REF = oracle.Ref() if oracle.have_ref() else None
+
+
+def ref_fft(x, inv):
+    if REF is not None and x.shape[-1] <= (1 << 23):
+        return REF.c2c(x, inv)
+    x64 = x.astype(np.complex128)
+    return np.fft.ifft(x64) * x.shape[-1] if inv else np.fft.fft(x64)
+
+
+def ref_fft2(x, inv):
+    if REF is not None:
+        return REF.fft2d(x, inv)
+    x64 = x.astype(np.complex128)
+    return np.fft.ifft2(x64) * x.size if inv else np.fft.fft2(x64)
 
 
 def one_d_cases(rank, world):
@@ -24,8 +44,7 @@ def one_d_cases(rank, world):
         cd = np.complex64 if dt == np.float32 else np.complex128
         rng = np.random.default_rng(lg)
         full = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(cd)
-        want_f = np.fft.fft(full.astype(np.complex128))
-        want_i = np.fft.ifft(full.astype(np.complex128)) * n
+        want_f, want_i = ref_fft(full, False), ref_fft(full, True)
         tol = (1e-6 if dt == np.float32 else 1e-14) * lg
         shard = torch.from_numpy(full[rank * n // world:(rank + 1) * n // world].copy()).cuda()
         for transport, bar in (("nccl", "collective"), ("p2p", "flags"), ("p2p", "collective")):
@@ -66,8 +85,7 @@ def main():
         rng = np.random.default_rng(w + h)
         full = (rng.uniform(-1, 1, (h, w)) + 1j * rng.uniform(-1, 1, (h, w))).astype(cd)
         hl, wp = h // world, w // world
-        want_f = np.fft.fft2(full.astype(np.complex128))
-        want_i = np.fft.ifft2(full.astype(np.complex128)) * (w * h)
+        want_f, want_i = ref_fft2(full, False), ref_fft2(full, True)
         tol = (1e-6 if dt == np.float32 else 1e-14) * np.log2(w * h)
         slab = torch.from_numpy(full[rank * hl:(rank + 1) * hl].copy()).cuda()
         # p2p: peer-memory flag barrier (default) and the collective-call barrier

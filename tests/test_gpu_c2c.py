@@ -5,6 +5,8 @@ Mirrors the structure of the reference's TestFFT_Pow2 (test/fft_test_impl.h:35-5
 round trip; tolerance is north_star's rel-L2 <= 1e-6*log2N (float) / 1e-14*log2N (double), and the
 reference's own absolute FFT_Eps (test/test_util.h:62-72) is checked as well.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -349,3 +351,99 @@ def test_c_loop_pair_timing_hook():
     torch.cuda.synchronize()
     assert g.launch_count() - n0 == 2 * (20 + 2) and us.value > 0
     assert float((z / n - x).abs().max()) < 1e-5
+
+
+@pytest.mark.no_emu  # needs real streams
+def test_chained_plan_on_two_streams_at_once(comparand):
+    """One chained (two-pass) plan executed on two streams concurrently: every stream has its own ticket / group
+    counters, so neither execution resets the other's mid-kernel (the counters used to be one per plan)."""
+    n, batch = 1 << 16, 64
+    rng = np.random.default_rng(11)
+    xa, xb = rand_cpx(rng, (batch, n), np.float32), rand_cpx(rng, (batch, n), np.float32)
+    plan = g.FFT(n, np.float32, batch=batch)
+    da, db = torch.from_numpy(xa).cuda(), torch.from_numpy(xb).cuda()
+    oa, ob = torch.empty_like(da), torch.empty_like(db)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(6):
+        with torch.cuda.stream(sa):
+            plan.forward(oa, da)
+        with torch.cuda.stream(sb):
+            plan.forward(ob, db)
+    torch.cuda.synchronize()
+    want_a = np.fft.fft(xa[:4].astype(np.complex128), axis=1)
+    assert oracle.rel_l2(oa[:4].cpu().numpy(), want_a) <= oracle.tolerance(n, np.float32)
+    ref_a, ref_b = torch.empty_like(da), torch.empty_like(db)
+    plan.forward(ref_a, da)
+    plan.forward(ref_b, db)
+    torch.cuda.synchronize()
+    assert torch.equal(oa, ref_a) and torch.equal(ob, ref_b)
+
+
+def test_host_pointers_pinned_chunked_two_pass(comparand, monkeypatch):
+    """Host-pointer execution of a chained two-pass plan from PINNED memory in several chunks: the chunks alternate
+    between two streams and really overlap, each with its own chain counters."""
+    monkeypatch.setenv("GENFFT_CUDA_HOST_CHUNK_MB", "1")
+    n, batch = 1 << 16, 24
+    x = torch.from_numpy(rand_cpx(np.random.default_rng(3), (batch, n), np.float32))
+    out = torch.empty_like(x)
+    if torch.cuda.is_available() and os.environ.get("GENFFT_TEST_BACKEND") != "emu":
+        x, out = x.pin_memory(), out.pin_memory()
+    plan = g.FFT(n, np.float32, batch=batch)
+    for rep in range(3):
+        plan.forward(out, x)
+    want = np.fft.fft(x.numpy().astype(np.complex128), axis=1)
+    assert oracle.rel_l2(out.numpy(), want) <= oracle.tolerance(n, np.float32)
+    assert oracle.rel_l2(out.numpy()[:2], comparand.c2c_batch(x.numpy()[:2])) <= oracle.tolerance(n, np.float32)
+
+
+def test_host_pointer_calls_from_several_threads_on_one_plan(comparand):
+    """The reference's impl objects are stateless and safe to call concurrently; the host-pointer path serialises per
+    plan instead of corrupting its staging buffers."""
+    import threading
+    n, batch = 4096, 8
+    plan = g.FFT(n, np.float32, batch=batch)
+    rng = np.random.default_rng(9)
+    xs = [rand_cpx(rng, (batch, n), np.float32) for _ in range(4)]
+    outs = [np.empty_like(x) for x in xs]
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                plan.forward(outs[k], xs[k])
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    for x, o in zip(xs, outs):
+        assert oracle.rel_l2(o, np.fft.fft(x.astype(np.complex128), axis=1)) <= oracle.tolerance(n, np.float32)
+
+
+def test_distances_smaller_than_a_transform_are_rejected():
+    for kw in (dict(in_dist=100), dict(out_dist=255), dict(in_dist=-256)):
+        with pytest.raises(g.GenfftCudaError):
+            g.FFT(256, np.float32, batch=4, **kw)
+    with pytest.raises(g.GenfftCudaError):
+        g.RealFFT(256, np.float32, half=True, batch=4, out_dist=100)
+    with pytest.raises(g.GenfftCudaError):
+        g.InverseRealFFT(256, np.float32, batch=4, out_dist=128)
+    g.FFT(256, np.float32, batch=1, in_dist=1)  # a single transform has no distance to violate
+    with pytest.raises(ValueError):
+        g.DIT(64, np.float32).apply(torch.zeros(8, dtype=torch.complex64, device="cuda"),
+                                    torch.zeros(32, dtype=torch.complex64, device="cuda"), False)
+    with pytest.raises(ValueError):
+        g.FFTVert(64, np.float32).transform_no_scramble(torch.zeros(64, dtype=torch.complex64, device="cuda"), 4, 4)
+
+
+def test_plan_is_bound_to_its_device():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    plan = g.FFT(1024, np.float32)
+    x = torch.zeros(1024, dtype=torch.complex64, device="cuda:1")
+    with torch.cuda.device(1):
+        with pytest.raises(g.GenfftCudaError):
+            plan.forward(torch.empty_like(x), x)

@@ -364,3 +364,34 @@ def test_half_spectrum_inverse(dt, n, batch):
     h_out = np.empty((batch, n), dtype=dt)
     inv.inverse(h_out, s)  # host pointers
     assert oracle.rel_l2(h_out, want) <= oracle.tolerance(n, dt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_half_spectrum_inverse_host_leaves_gaps_alone(dt):
+    """Host-pointer c2r with out_dist > n writes the n real points of every transform and nothing between them."""
+    n, batch, out_dist = 256, 5, 262
+    rng = np.random.default_rng(2)
+    s = (rng.uniform(-1, 1, (batch, n // 2 + 1)) + 1j * rng.uniform(-1, 1, (batch, n // 2 + 1))).astype(CPX[dt])
+    s[:, 0] = s[:, 0].real
+    s[:, -1] = s[:, -1].real
+    out = np.full((batch, out_dist), 42.5, dtype=dt)
+    g.InverseRealFFT(n, dt, batch=batch, out_dist=out_dist).inverse(out, s)
+    want = np.fft.irfft(s.astype(np.complex128), n=n, axis=1) * n
+    assert oracle.rel_l2(out[:, :n], want) <= oracle.tolerance(n, dt)
+    assert np.all(out[:, n:] == 42.5)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_separate_on_host_pointers(comparand, dt):
+    """separate_2x_real_FFT on host arrays goes through the C ABI (genfft_cuda_separate_2x_real), aliasing allowed."""
+    n = 512
+    rng = np.random.default_rng(8)
+    a, b = rng.uniform(-1, 1, n).astype(dt), rng.uniform(-1, 1, n).astype(dt)
+    z = np.empty(n, CPX[dt])
+    g.FFT(n, dt).transform_interleave(z, a, b)
+    fa, fb = np.empty_like(z), np.empty_like(z)
+    g.separate_2x_real_FFT(fa, fb, z, n)
+    ra, rb = comparand.two_real(a, b)
+    assert oracle.rel_l2(fa, ra) <= oracle.tolerance(n, dt) and oracle.rel_l2(fb, rb) <= oracle.tolerance(n, dt)
+    g.separate_2x_real_FFT(z, fb, z, n)
+    assert np.array_equal(z, fa)

@@ -28,7 +28,7 @@ def rand_c(rng, shape, dt):
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("w,h", [(8, 8), (64, 16), (256, 512), (1024, 64), (32768, 8)])
 @pytest.mark.parametrize("inv", [False, True])
-def test_fft2d_slabs_p2p(dt, world, w, h, inv):
+def test_fft2d_slabs_p2p(comparand, dt, world, w, h, inv):
     if w % world or h % world:
         pytest.skip("shape not divisible by the number of ranks")
     rng = np.random.default_rng(w * 31 + h)
@@ -45,15 +45,14 @@ def test_fft2d_slabs_p2p(dt, world, w, h, inv):
         eng[r].cols_to_peers(blocks[r].data_ptr(), [o.data_ptr() for o in outs], r, inv)
     torch.cuda.synchronize()
     got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
-    x64 = x.astype(np.complex128)
-    want = np.fft.ifft2(x64) * (w * h) if inv else np.fft.fft2(x64)
+    want = comparand.fft2d(x, inv)  # genFFT's own FFT2D::transform<inv> (fft.h:213-241)
     assert oracle.rel_l2(got, want) <= oracle.tolerance(w * h, dt)
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("w,h", [(64, 16), (512, 256)])
-def test_fft2d_slabs_packed_transport(dt, world, w, h):
+def test_fft2d_slabs_packed_transport(comparand, dt, world, w, h):
     """The NCCL transport's local kernels: rows_pack -> (all-to-all played by a host permutation) -> cols -> unpack."""
     rng = np.random.default_rng(w + h)
     x = rand_c(rng, (h, w), dt)
@@ -73,7 +72,7 @@ def test_fft2d_slabs_packed_transport(dt, world, w, h):
         outs2.append(bo)
     torch.cuda.synchronize()
     got_t = np.concatenate([o.cpu().numpy() for o in outs2], axis=1)  # transposed-output mode: (H x W) by column blocks
-    want = np.fft.fft2(x.astype(np.complex128))
+    want = comparand.fft2d(x)
     assert oracle.rel_l2(got_t, want) <= oracle.tolerance(w * h, dt)
     for r in range(world):  # second all-to-all + unpack into the natural-order row slab
         recv = torch.stack([outs2[g][r * hl:(r + 1) * hl] for g in range(world)], dim=0).contiguous()
@@ -87,7 +86,7 @@ def test_fft2d_slabs_packed_transport(dt, world, w, h):
 @pytest.mark.parametrize("world", [1, 2, 4])
 @pytest.mark.parametrize("lg", [6, 11, 16])
 @pytest.mark.parametrize("inv", [False, True])
-def test_four_step_1d_p2p(dt, world, lg, inv):
+def test_four_step_1d_p2p(comparand, dt, world, lg, inv):
     """DistFFT1D's p2p phases (strided peer copy, column pass + scatter, twiddle, row pass + scatter, transpose)."""
     n = 1 << lg
     h, w = four_step_shape(n, world)
@@ -109,8 +108,7 @@ def test_four_step_1d_p2p(dt, world, lg, inv):
         eng[r].twiddle(mids[r], r * hl, inv)
         eng[r].rows_to_peers(mids[r], [b.data_ptr() for b in blocks2], r, inv)
     torch.cuda.synchronize()
-    x64 = x.astype(np.complex128)
-    want = np.fft.ifft(x64) * n if inv else np.fft.fft(x64)
+    want = comparand.c2c(x, inv)  # genFFT's own FFT::transform<inv> (fft.h:80-85)
     z = np.concatenate([b.cpu().numpy() for b in blocks2], axis=1)  # Z[kr][kc] = X[kr + H kc]
     assert oracle.rel_l2(z, want.reshape(w, h).T) <= oracle.tolerance(n, dt)
     outs = []

@@ -84,9 +84,12 @@ _SIGNATURES = {
     "genfft_cuda_twiddle2d_dev": (C.c_int, [C.c_int, _vp, _i64, _i64, _i64, _i64, _i64, C.c_int, _vp]),
     "genfft_cuda_transpose_dev": (C.c_int, [C.c_int, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "genfft_cuda_debug_fast_div": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "genfft_cuda_debug_mode_launch_count": (C.c_uint64, [C.c_int]),
     "genfft_cuda_debug_time_c2c_pairs": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.POINTER(C.c_double)]),
     "genfft_cuda_peer_barrier_dev": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint32, _vp]),
     "genfft_cuda_memset_dev": (C.c_int, [_vp, C.c_int, C.c_size_t]),
+    "genfft_cuda_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
+    "genfft_cuda_host_free": (C.c_int, [_vp]),
     "genfft_cuda_malloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "genfft_cuda_free": (C.c_int, [_vp]),
     "genfft_cuda_ipc_get_handle": (C.c_int, [_vp, C.c_char_p]),

@@ -5,8 +5,14 @@
 // overlap (PCIe is full duplex and the copy engines are independent of the SMs).
 #include <cuda_runtime.h>
 
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
+#include <map>
 
 #include "../../include/genfft_cuda.h"
 #include "plan.h"
@@ -97,6 +103,77 @@ static int exec_batched_host(Plan* p, void* out, const void* in, size_t in_elem,
                                (size_t)nb, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < nbuf; s++) HX_TRY(cudaStreamSynchronize(p->streams[s]));
+  return GENFFT_CUDA_OK;
+}
+
+// ---- page-locked host buffers on the NUMA node of the current device ------------------------------------------------
+// The host-pointer path moves every byte across PCIe twice, so where the CALLER's buffers live decides its rate: on a
+// two-socket multi-GPU host a buffer on the other socket also crosses the socket interconnect, and with one process
+// per GPU all links are busy at once.  genfft_cuda_host_alloc maps anonymous memory, binds it to the GPU's node
+// (mbind), touches it and registers it with CUDA -- no CPU of that node is needed in the process's cpuset.
+namespace {
+std::mutex g_host_mu;
+std::map<void*, size_t> g_host_blocks;
+
+int numa_node_of_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) return -1;
+  for (char* c = bus; *c; c++)
+    if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+}  // namespace
+
+extern "C" int genfft_cuda_host_alloc(void** ptr, size_t bytes, int numa_local, int* numa_node_out) {
+  if (!ptr || !bytes) return set_error(GENFFT_CUDA_ERR_ARG, "null pointer or zero size");
+  const size_t len = (bytes + 4095) & ~(size_t)4095;
+  void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return set_error(GENFFT_CUDA_ERR_ALLOC, "mmap of the host buffer failed");
+  int node = numa_local ? numa_node_of_current_device() : -1;
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / 64] = 1ul << (node % 64);
+    // MPOL_PREFERRED (1): falls back to another node instead of failing when the node is not in the cpuset's mems
+    if (syscall(SYS_mbind, p, len, 1, mask, sizeof mask * 8 + 1, 0) != 0) node = -1;
+  } else {
+    node = -1;
+  }
+  for (size_t off = 0; off < len; off += 4096) static_cast<volatile char*>(p)[off] = 0;  // commit the pages there
+  cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    munmap(p, len);
+    return set_error(GENFFT_CUDA_ERR_CUDA, cudaGetErrorString(e));
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    g_host_blocks[p] = len;
+  }
+  if (numa_node_out) *numa_node_out = node;
+  *ptr = p;
+  return GENFFT_CUDA_OK;
+}
+
+extern "C" int genfft_cuda_host_free(void* ptr) {
+  if (!ptr) return GENFFT_CUDA_OK;
+  size_t len = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host_blocks.find(ptr);
+    if (it == g_host_blocks.end()) return set_error(GENFFT_CUDA_ERR_ARG, "not a genfft_cuda_host_alloc block");
+    len = it->second;
+    g_host_blocks.erase(it);
+  }
+  cudaHostUnregister(ptr);
+  munmap(ptr, len);
   return GENFFT_CUDA_OK;
 }
 

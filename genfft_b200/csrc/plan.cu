@@ -32,6 +32,7 @@ namespace genfft_cuda {
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_mode_launches[16];  // per compiled addressing mode (tests: "the specialised mode really ran")
 
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -375,6 +376,43 @@ static int pass_stage_table(int device, int precision, int P, long long Ns, int 
   return GENFFT_CUDA_OK;
 }
 
+// whole inter-pass table of a pass with Ns * L = M small enough to stay in L2: entry [k][p] = W_M^(p*k), k < L, p < Ns
+static std::map<std::tuple<int, int, long long, long long>, void*> g_direct_tables;
+
+static int direct_pass_table(int device, int precision, long long Ns, long long L, const void** out) {
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_tuple(device, precision, Ns, L);
+  auto it = g_direct_tables.find(key);
+  if (it != g_direct_tables.end()) {
+    *out = it->second;
+    return GENFFT_CUDA_OK;
+  }
+  const size_t es = elem_size(precision);
+  const unsigned long long M = (unsigned long long)Ns * (unsigned long long)L;
+  std::vector<unsigned char> host(es * (size_t)M);
+  for (long long k = 0; k < L; k++)
+    for (long long q = 0; q < Ns; q++) {
+      long double c, sn;
+      unit_root(((unsigned long long)q * (unsigned long long)k) % M, M, &c, &sn);
+      const size_t e = (size_t)k * (size_t)Ns + (size_t)q;
+      if (precision == GENFFT_CUDA_F32) {
+        float* t = reinterpret_cast<float*>(host.data()) + 2 * e;
+        t[0] = (float)c;
+        t[1] = (float)-sn;
+      } else {
+        double* t = reinterpret_cast<double*>(host.data()) + 2 * e;
+        t[0] = (double)c;
+        t[1] = (double)-sn;
+      }
+    }
+  void* d = nullptr;
+  CU_TRY(cudaMalloc(&d, host.size()));
+  CU_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+  g_direct_tables[key] = d;
+  *out = d;
+  return GENFFT_CUDA_OK;
+}
+
 // two-level table for W_M^e, e < M: W = hi[e >> shift] * lo[e & (2^shift - 1)]
 static int two_level_table(int device, int precision, long long M, const void** hi, const void** lo, int* shift) {
   const int lg = ilog2(M);
@@ -434,6 +472,11 @@ static int build_seq(Seq* seq, int device, int precision, long long N, bool wide
       // W_{P*Ns}^(p*i), i < P, p < Ns
       rc = pass_stage_table(device, precision, ps.k->P, Ns, ps.k->C, &ps.tw_b);
       if (rc) return rc;
+      // small M: the whole table W_M^(p*k) is read directly (2 MiB at 2^18 single precision: L2-resident)
+      if (ilog2(Ns * ps.R) <= env_int("GENFFT_CUDA_DIRECT_TW_LOG2", 18)) {
+        rc = direct_pass_table(device, precision, Ns, ps.R, &ps.tw_d);
+        if (rc) return rc;
+      }
     }
     seq->passes.push_back(ps);
     Ns *= ps.R;
@@ -460,6 +503,7 @@ static PassParams base_params(const PassSpec& ps, const void* in, void* out, int
   p.tw_shift = ps.tw_shift;
   p.tw_b = ps.tw_b;
   p.tw_b_stride = ps.Ns;
+  p.tw_d = ps.tw_d;
   return p;
 }
 
@@ -632,6 +676,7 @@ static int resolve_pass(const Plan* plan, const PassSpec& ps, const PassParams& 
     r->grid = (int)std::min<long long>(((long long)p.ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta, 0x7fffffffLL);
   }
   r->launch = ps.k->launch[mode][inv];
+  r->mode = mode;
   return GENFFT_CUDA_OK;
 }
 
@@ -642,6 +687,7 @@ static int launch_pass(const Plan* plan, const PassSpec& ps, const PassParams& p
   if (!r.launch) return GENFFT_CUDA_OK;
   r.launch(r.q, r.grid, stream);
   g_launches++;
+  g_mode_launches[r.mode & 15]++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
 }
@@ -720,6 +766,8 @@ static int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaS
   CU_TRY(cudaMemsetAsync(ctr, 0, need * sizeof(uint32_t), stream));
   ce->launch(cp, (unsigned)std::min(total, resident), stream);
   g_launches++;
+  g_mode_launches[ce->ma & 15]++;
+  g_mode_launches[ce->mb & 15]++;
   CU_TRY(cudaGetLastError());
   return GENFFT_CUDA_OK;
 }
@@ -948,6 +996,7 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
       p.dit_tw = df->dit_tw;
     }
     if (fs && s == n - 1) {
+      const int twiddled_mode = p.mode;  // what the pass would be without the redirected store
       p.mode = M_GEN;
       const long long Ns = (st.N == st.ps->R) ? 1 : st.ps->Ns;
       const int sh = fs->part_log2 - ilog2(Ns);
@@ -957,6 +1006,12 @@ static int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, Vie
         p.use_peers = 1;
         for (int g = 0; g < fs->npeers && g < kMaxPeers; g++)
           p.out_peer[g] = (char*)fs->peers[g] + (size_t)(fs->peer_offset + off(io[s].dst)) * es;
+        // the last pass of a multi-pass transform split over 2 / 4 / 8 ranks: bin k goes to rank k >> log2(L / ranks),
+        // which the compile-time peer modes resolve per register (tile_kernel.cuh, M_PEER*)
+        const int pm = fs->npeers == 2 ? M_PEER2 : fs->npeers == 4 ? M_PEER4 : fs->npeers == 8 ? M_PEER8 : -1;
+        if (pm >= 0 && twiddled_mode == M_COLTW && !st.brev && !st.real_in && st.ps->k->launch[pm][inverse ? 1 : 0] &&
+            (1LL << sh) * fs->npeers == st.ps->R && env_int("GENFFT_CUDA_PEER_MODES", 1))
+          p.mode = pm;
       } else {
         p.out_stride_khi = fs->part_stride;
       }
@@ -1265,6 +1320,7 @@ int genfft_cuda_device_count(void) {
 }
 
 uint64_t genfft_cuda_launch_count(void) { return g_launches.load(); }
+uint64_t genfft_cuda_debug_mode_launch_count(int mode) { return mode >= 0 && mode < 16 ? g_mode_launches[mode].load() : 0; }
 
 // host evaluation of the kernels' division-free tile decode (tile_kernel.cuh: fast_div), for the CPU test suite
 uint32_t genfft_cuda_debug_fast_div(uint32_t x, uint32_t d) {

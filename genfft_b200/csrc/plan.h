@@ -21,6 +21,7 @@ struct PassSpec {
   const void* tw_lo = nullptr;
   int tw_shift = 0;
   const void* tw_b = nullptr;   // W_{P*Ns}^(p*i) laid out [i][p]
+  const void* tw_d = nullptr;   // whole table W_{Ns*R}^(p*k) laid out [k][p] when Ns*R is small (read instead of the three above)
 };
 
 // decomposition of one length-N transform
@@ -34,6 +35,7 @@ struct Seq {
 struct ResolvedLaunch {
   PassParams q;
   int grid = 0;
+  int mode = 0;
   void (*launch)(const PassParams& prm, int grid, cudaStream_t stream) = nullptr;
 };
 

@@ -8,7 +8,7 @@
 
 namespace genfft_cuda {
 
-constexpr int kNumModes = 8;
+constexpr int kNumModes = 11;
 
 struct KernelEntry {
   int L, P, C;
@@ -68,6 +68,11 @@ KernelEntry make_entry() {
     add_mode<T, L, P, C, M_COLTW>(e);
     add_mode<T, L, P, C, M_FIRST>(e);
     if constexpr (C >= 2 && L >= 16) add_mode<T, L, P, C, M_COLTWDIT>(e);
+    if constexpr (P == 16 && L >= 64) {  // last pass of a distributed transform: the store is the all-to-all
+      add_mode<T, L, P, C, M_PEER2>(e);
+      add_mode<T, L, P, C, M_PEER4>(e);
+      add_mode<T, L, P, C, M_PEER8>(e);
+    }
   }
   return e;
 }
@@ -105,6 +110,14 @@ void add_chain(std::vector<ChainEntry>& v) {
   v.push_back(e);
 }
 
+template <typename T, int LA, int CA, int LB, int CB, int MB>
+void add_peer_chains(std::vector<ChainEntry>& v) {
+  add_chain<T, LA, CA, M_FIRST, LB, CB, MB, false>(v);
+  add_chain<T, LA, CA, M_FIRST, LB, CB, MB, true>(v);
+  add_chain<T, LA, CA, M_COL, LB, CB, MB, false>(v);
+  add_chain<T, LA, CA, M_COL, LB, CB, MB, true>(v);
+}
+
 // every mode pair the plans chain, for one pair of shapes
 template <typename T, int LA, int CA, int LB, int CB>
 void add_chain_shapes(std::vector<ChainEntry>& v) {
@@ -120,6 +133,9 @@ void add_chain_shapes(std::vector<ChainEntry>& v) {
   add_chain<T, LA, CA, M_FIRST, LB, CB, M_GEN, true>(v);
   add_chain<T, LA, CA, M_COL, LB, CB, M_GEN, false>(v);
   add_chain<T, LA, CA, M_COL, LB, CB, M_GEN, true>(v);
+  add_peer_chains<T, LA, CA, LB, CB, M_PEER2>(v);  // ... through the compile-time peer modes (p2p transport)
+  add_peer_chains<T, LA, CA, LB, CB, M_PEER4>(v);
+  add_peer_chains<T, LA, CA, LB, CB, M_PEER8>(v);
 }
 
 // defined in chains_inst.cu (compiled once per GENFFT_CSET)

@@ -64,6 +64,10 @@ struct PassParams {
   int tw_shift;
   const void* tw_b;
   long long tw_b_stride;  // = Ns
+  // ... or, when M is small enough for the whole table to stay in L2 (plan.cu: GENFFT_CUDA_DIRECT_TW_LOG2), read
+  // directly: tw_d[k*Ns + p] = W_M^(p*k), k < L, p < Ns -- one load and one multiply per point instead of the
+  // factored form's two multiplies, and one rounding instead of three.  Lanes read consecutive p (coalesced).
+  const void* tw_d;
   // fused real-FFT split (M_ROWDIT): the tile's L-point complex transforms are the packed halves of 2L-point
   // real signals; dit_tw[k] = W_{2L}^k, k < L; dit_half: write L+1 bins only, else all 2L
   const void* dit_tw;
@@ -136,7 +140,13 @@ __host__ __device__ constexpr int tile_pitch_t(int L) { return pad_idx_t<PADSH>(
 //   M_ROWDIT: M_ROW + the real-FFT split fused after the last butterfly stage    (RealFFT<T>, n <= 2*Lmax)
 //   M_COLTWDIT: last pass of a large real transform: M_COLTW on a PAIR of column groups {p} and {Ns-p} so that the
 //             real-FFT split, which couples bins q and M-q, is fused after the last butterfly stage
-enum Mode { M_GEN = 0, M_ROW = 1, M_COL = 2, M_COLTW = 3, M_FIRST = 4, M_ROWTMA = 5, M_ROWDIT = 6, M_COLTWDIT = 7 };
+//   M_PEER2/4/8: M_COLTW whose store is the all-to-all of the distributed transforms: the last pass of a length-N
+//             transform split over NP ranks sends bin k = u + i*TN to rank k / (L/NP) = i / (16/NP) -- a compile-time
+//             function of the register index -- so a thread's 16 stores are NP groups of 16/NP stores at immediate
+//             multiples of one stride from NP peer bases (CUDA-IPC mapped buffers, NVLink stores)
+enum Mode { M_GEN = 0, M_ROW = 1, M_COL = 2, M_COLTW = 3, M_FIRST = 4, M_ROWTMA = 5, M_ROWDIT = 6, M_COLTWDIT = 7,
+            M_PEER2 = 8, M_PEER4 = 9, M_PEER8 = 10 };
+__host__ __device__ constexpr int peer_mode_ranks(int mode) { return mode == M_PEER2 ? 2 : mode == M_PEER4 ? 4 : mode == M_PEER8 ? 8 : 0; }
 
 // Division of a tile index (< 2^31) by a launch-invariant divisor d without the ~25-instruction software division:
 // host side  shr = ceil(log2 d) - 1, mul = ceil(2^(32 + shr) / d)  (d >= 2; mul = 0 encodes d == 1),
@@ -278,6 +288,8 @@ struct TileKernel {
   static constexpr bool TMA = MODE == M_ROWTMA;
   static constexpr bool DIT = MODE == M_ROWDIT;
   static constexpr bool PAIR = MODE == M_COLTWDIT;
+  static constexpr int NPEER = peer_mode_ranks(MODE);
+  static constexpr bool PEER = NPEER > 0;
   static constexpr int HALF_C = C / 2;
   static constexpr bool ROWLIKE = MODE == M_ROW || TMA || DIT;
   static constexpr size_t XBUF_BYTES = (NST > 1 || DIT || PAIR) ? sizeof(cpx<T>) * (size_t)PITCH * C : 0;
@@ -346,6 +358,16 @@ struct TileKernel {
   static __device__ __forceinline__ void apply_pass_twiddle(const PassParams& prm, const Tile& t, uint32_t col, int u,
                                                             cpx<T> (&x)[P]) {
     const uint32_t p = (t.p_base + col * (uint32_t)prm.p_c) & prm.p_mask;
+    if (prm.tw_d) {  // uniform branch: the whole launch takes the same side
+      const uint32_t ns32 = (uint32_t)prm.tw_b_stride;
+      const V* td = reinterpret_cast<const V*>(prm.tw_d) + ((size_t)(uint32_t)u * ns32 + p);
+      V w[P];
+#pragma unroll
+      for (int i = 0; i < P; i++) w[i] = ldg_strided(td, ns32, (uint32_t)(i * TN));
+#pragma unroll
+      for (int i = 0; i < P; i++) x[i] = cmul(x[i], cpx<T>(w[i].x, w[i].y));
+      return;
+    }
     const V* hi = reinterpret_cast<const V*>(prm.tw_hi);
     const V* lo = reinterpret_cast<const V*>(prm.tw_lo);
     const uint32_t e = p * (uint32_t)u;
@@ -400,7 +422,7 @@ struct TileKernel {
 #pragma unroll
         for (int i = 0; i < P; i++) x[i] = cpx<T>(T(0), T(0));
       }
-      if constexpr (MODE == M_COLTW || PAIR) apply_pass_twiddle(prm, t, col, u, x);
+      if constexpr (MODE == M_COLTW || PAIR || PEER) apply_pass_twiddle(prm, t, col, u, x);
     } else {
     const long long base = t.in_off + (long long)col * prm.in_stride_c;
 #pragma unroll
@@ -445,7 +467,7 @@ struct TileKernel {
 #pragma unroll
       for (int i = 0; i < P; i++) x[i].y = -x[i].y;
     }
-    if (prm.tw_hi) apply_pass_twiddle(prm, t, col, u, x);
+    if (prm.tw_hi || prm.tw_d) apply_pass_twiddle(prm, t, col, u, x);
     }
   }
 
@@ -454,7 +476,23 @@ struct TileKernel {
     const uint32_t col = t.col0 + c;
     if (col >= (uint32_t)prm.ncols) return;
     const long long base = t.out_off + (long long)col * prm.out_stride_c;
-    if constexpr (!GEN) {
+    if constexpr (PEER) {
+      static_assert(!PEER || (P == 16 && NST >= 1), "peer modes are built for 16 points per thread");
+      constexpr int G = P / (NPEER ? NPEER : 1);  // consecutive register slots that go to the same rank
+      const uint32_t s32 = (uint32_t)prm.out_stride_k;
+      const long long off = base + (long long)u * prm.out_stride_k;
+#pragma unroll
+      for (int g = 0; g < NPEER; g++) {
+        V* dst = reinterpret_cast<V*>(prm.out_peer[g]) + off;
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+          V v;
+          v.x = x[g * G + j].x;
+          v.y = INV ? -x[g * G + j].y : x[g * G + j].y;
+          st_strided<CO_DEFAULT>(dst, s32, (uint32_t)(j * TN), v);
+        }
+      }
+    } else if constexpr (!GEN) {
       if constexpr (UNIT_OUT) {
         V* dst = reinterpret_cast<V*>(prm.out) + base + u;
 #pragma unroll

@@ -160,6 +160,13 @@ int genfft_cuda_exec_dit(genfft_cuda_plan_t plan, void* out, const void* in, int
 /* separate_2x_real_FFT(out1, out2, in, N) (FFTReal.h:35-66) on host pointers; out1 or out2 may alias in. */
 int genfft_cuda_separate_2x_real(int precision, void* out1, void* out2, const void* in, int64_t n);
 
+/* Page-locked host buffers for the entry points above, placed on the NUMA node of the current device when
+ * numa_local != 0 (mmap + mbind + cudaHostRegister; *numa_node_out = the node, or -1 when it could not be bound).
+ * The host-pointer path is PCIe-bound, so on a two-socket multi-GPU host the placement of the caller's buffers
+ * decides its rate.  Nothing in the reference corresponds to this (genFFT never leaves the CPU). */
+int genfft_cuda_host_alloc(void** ptr, size_t bytes, int numa_local, int* numa_node_out);
+int genfft_cuda_host_free(void* ptr);
+
 /* ---- distributed 2D building blocks (slab decomposition; one process per GPU) ---------------------------
  * The host side (genfft_b200/dist.py) owns the process group; these run the local passes.
  *
@@ -198,6 +205,10 @@ int genfft_cuda_twiddle2d_dev(int precision, void* data, int64_t stride, int64_t
                               int64_t n_total, int inverse, void* stream);
 int genfft_cuda_transpose_dev(int precision, void* out, int64_t out_stride, const void* in, int64_t in_stride,
                               int64_t rows, int64_t cols, void* stream);
+
+/* Test hook: launches so far of the kernels compiled for addressing mode `mode` (tile_kernel.cuh enum Mode; a chained
+ * launch counts for both of its passes) -- lets a test assert that a specialised mode, not the generic one, ran. */
+uint64_t genfft_cuda_debug_mode_launch_count(int mode);
 
 /* Test hook: x / d as the kernels compute it when they decode a tile index (magic-number multiply, exact for
  * x < 2^31); host code only. */

@@ -19,6 +19,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 
@@ -139,3 +140,7 @@ template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultipro
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+enum { cudaHostRegisterDefault = 0 };
+inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetPCIBusId(char* s, int n, int) { snprintf(s, n, "0000:00:00.0"); return cudaSuccess; }

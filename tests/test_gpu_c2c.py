@@ -447,3 +447,19 @@ def test_plan_is_bound_to_its_device():
     with torch.cuda.device(1):
         with pytest.raises(g.GenfftCudaError):
             plan.forward(torch.empty_like(x), x)
+
+
+def test_host_buffers_near_the_gpu(comparand):
+    """genfft_cuda_host_alloc (page-locked, bound to the GPU's NUMA node when the host has several) as the caller's
+    buffers of the host-pointer path."""
+    from genfft_b200.hostmem import PinnedNearGpu
+    n, batch = 4096, 16
+    bx, by = PinnedNearGpu((batch, n), np.complex64), PinnedNearGpu((batch, n), np.complex64)
+    assert bx.numa_node >= -1 and bx.array.shape == (batch, n)
+    bx.array[...] = rand_cpx(np.random.default_rng(4), (batch, n), np.float32)
+    g.FFT(n, np.float32, batch=batch).forward(by.array, bx.array)
+    assert oracle.rel_l2(by.array, comparand.c2c_batch(bx.array)) <= oracle.tolerance(n, np.float32)
+    ptr = bx.ptr
+    bx.close()
+    by.close()
+    assert g.lib().genfft_cuda_host_free(ptr) != 0  # not (or no longer) one of its blocks: an error, not a crash

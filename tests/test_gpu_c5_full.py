@@ -39,7 +39,7 @@ def test_c5_full_size_vs_reference(checkers, inv):
     x = torch.view_as_complex(torch.rand((H, W, 2), generator=gen, device="cuda") * 2 - 1)
     y = torch.empty_like(x)
     plan = g.FFT2D(W, H, np.float32)
-    plan.transform(y, x, inv)
+    plan.transform(y, x, inv=inv)
     torch.cuda.synchronize()
 
     # rows by the reference, keeping the sampled columns only

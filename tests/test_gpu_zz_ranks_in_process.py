@@ -119,3 +119,32 @@ def test_four_step_1d_p2p(comparand, dt, world, lg, inv):
     torch.cuda.synchronize()
     got = np.concatenate([o.cpu().numpy().reshape(-1) for o in outs])
     assert oracle.rel_l2(got, want) <= oracle.tolerance(n, dt)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("inv", [False, True])
+def test_peer_modes_run_and_match_the_generic_store(monkeypatch, world, inv):
+    """The last pass of a multi-pass distributed transform runs in the compile-time peer modes (M_PEER2/4/8,
+    tile_kernel.cuh) -- not in the run-time generic mode -- and stores bit-identical results."""
+    from genfft_b200 import lib
+    w, h, dt = 32768, 8, np.float32
+    mode = {2: 8, 4: 9, 8: 10}[world]
+    x = rand_c(np.random.default_rng(world), (h, w), dt)
+    hl, wp = h // world, w // world
+
+    def run():
+        eng = [CudaSlabEngine(w, h, world, dt) for _ in range(world)]
+        blocks = [torch.full((h, wp), float("nan"), dtype=TCPX[dt], device="cuda") for _ in range(world)]
+        for r in range(world):
+            eng[r].rows_to_peers(torch.from_numpy(x[r * hl:(r + 1) * hl]).cuda(), [b.data_ptr() for b in blocks], r, inv)
+        torch.cuda.synchronize()
+        return torch.cat(blocks, dim=1)
+
+    n0 = lib().genfft_cuda_debug_mode_launch_count(mode)
+    fast = run()
+    assert lib().genfft_cuda_debug_mode_launch_count(mode) - n0 == world
+    monkeypatch.setenv("GENFFT_CUDA_PEER_MODES", "0")
+    g0 = lib().genfft_cuda_debug_mode_launch_count(0)
+    generic = run()
+    assert lib().genfft_cuda_debug_mode_launch_count(0) - g0 == world
+    assert torch.equal(fast, generic)

@@ -309,7 +309,7 @@ struct PeerBarrierParams {
 };
 
 #ifndef GENFFT_EMU
-__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerBarrierParams p) {
+static __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerBarrierParams p) {
   const int r = threadIdx.x;
   if (r >= p.world) return;
   __threadfence_system();

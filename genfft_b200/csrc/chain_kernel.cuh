@@ -2,7 +2,7 @@
 // the intermediate never makes the round trip through HBM.
 //
 // The data is cut into groups of a few MiB whose B tiles depend only on the A tiles of the same group (whole rows /
-// columns / transforms, or the column classes p mod R of a three-pass transform, see plan.cu).  A persistent grid of
+// columns / transforms, or the column classes p mod R of a three-pass transform, see pass_chain.cu).  A persistent grid of
 // CTAs takes tiles from an atomic ticket counter in the order
 //     A(0) .. A(lag-1) | A(s) interleaved 1:1 with B(s-lag), s = lag .. ngroups-1 | B(ngroups-lag) .. B(ngroups-1)
 // so the chip always works on an HBM-bound pass (A reads its input from HBM) and on an L2-bound pass (B reads what

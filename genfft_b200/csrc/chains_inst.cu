@@ -1,5 +1,5 @@
 // Explicit instantiations of the pass-chain kernel (chain_kernel.cuh) for the pairs of wide shapes the plans produce
-// (plan.cu: build_seq splits log2 N as evenly as possible, find_kernel picks ~256-thread CTAs in float and
+// (planner.cu: build_seq splits log2 N as evenly as possible, find_kernel picks ~256-thread CTAs in float and
 // ~128-thread CTAs in double).  Compiled once per GENFFT_CSET so the sets build in parallel.
 #include "registry.h"
 

@@ -64,7 +64,7 @@ struct PassParams {
   int tw_shift;
   const void* tw_b;
   long long tw_b_stride;  // = Ns
-  // ... or, when M is small enough for the whole table to stay in L2 (plan.cu: GENFFT_CUDA_DIRECT_TW_LOG2), read
+  // ... or, when M is small enough for the whole table to stay in L2 (planner.cu: GENFFT_CUDA_DIRECT_TW_LOG2), read
   // directly: tw_d[k*Ns + p] = W_M^(p*k), k < L, p < Ns -- one load and one multiply per point instead of the
   // factored form's two multiplies, and one rounding instead of three.  Lanes read consecutive p (coalesced).
   const void* tw_d;

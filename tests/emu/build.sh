@@ -7,6 +7,7 @@ SRC="$HERE/../../genfft_b200/csrc"
 OUT="${GENFFT_EMU_OUT:-$HERE/_build}"
 OBJ="$OUT/obj"
 mkdir -p "$OBJ"
+rm -f "$OBJ/plan.o"
 CXX=${CXX:-g++}
 FLAGS="-std=c++17 ${GENFFT_EMU_OPT:--O1} $GENFFT_EMU_EXTRA -fPIC -DGENFFT_EMU=1 -I$HERE/shim -Wno-unknown-pragmas -Wno-attributes -x c++"
 pids=()
@@ -16,7 +17,9 @@ done
 for k in 0 1 2 3 4 5; do
   $CXX $FLAGS -DGENFFT_KSET=$k -c "$SRC/kernels_inst.cu" -o "$OBJ/kernels_$k.o" & pids+=($!)
 done
-$CXX $FLAGS -c "$SRC/plan.cu" -o "$OBJ/plan.o" & pids+=($!)
+for f in planner pass_chain abi; do
+  $CXX $FLAGS -c "$SRC/$f.cu" -o "$OBJ/$f.o" & pids+=($!)
+done
 $CXX $FLAGS -c "$SRC/host_exec.cu" -o "$OBJ/host_exec.o" & pids+=($!)
 $CXX $FLAGS -c "$HERE/emu_runtime.cpp" -o "$OBJ/emu_runtime.o" & pids+=($!)
 for p in "${pids[@]}"; do wait $p; done

@@ -82,7 +82,7 @@ inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 
-// ---- runtime API (the subset plan.cu / host_exec.cu call) ---------------------------------------------------------------
+// ---- runtime API (the subset planner.cu / pass_chain.cu / abi.cu / host_exec.cu call) ---------------------------------------------------------------
 enum cudaError_t { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
 inline const char* cudaGetErrorString(cudaError_t e) {
   return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory (emulated)" : "invalid value (emulated)";

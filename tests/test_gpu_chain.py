@@ -182,7 +182,7 @@ EXPERIMENTAL = os.environ.get("GENFFT_TEST_BACKEND") == "emu" or os.environ.get(
 def test_r2c_chain_of_the_first_two_passes(lg, batch, half, env):
     """GENFFT_CUDA_CHAIN12=1: when the last two passes of a three-pass real transform cannot be chained (the fused-split
     pass pairs bins across the whole transform), the first two run as one chain whose groups are pass 2's blocks a and
-    pass 1's columns a + i*R3 (plan.cu: try_chain_first_two).  Same bits as the passes one by one, one launch less."""
+    pass 1's columns a + i*R3 (pass_chain.cu: try_chain_first_two).  Same bits as the passes one by one, one launch less."""
     if lg >= 22 and os.environ.get("GENFFT_TEST_BACKEND") == "emu":
         pytest.skip("too large for the emulator's time budget")
     n = 1 << lg

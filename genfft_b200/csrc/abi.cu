@@ -618,9 +618,8 @@ int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in,
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = p->n, M = n / 2;
   const size_t es = elem_size(p->precision);
-#ifdef GENFFT_FUSED_C2R
-  // variant: no pre-process pass and no staging -- the first butterfly pass reads X[s] and X[M - s] itself
-  if (!p->seq.passes.empty() && env_int("GENFFT_CUDA_FUSED_C2R", 1)) {
+  // no pre-process pass and no staging: the first butterfly pass reads X[s] and X[M - s] itself (in_real == 3)
+  if (!p->seq.passes.empty()) {
     std::vector<Step> steps;
     seq_steps(p->seq, false, steps, false, false);
     steps[0].c2r = true;
@@ -628,8 +627,7 @@ int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in,
     View vin{const_cast<void*>(in), p->in_dist}, vout{out, p->out_dist / 2};
     return run_chain(p, steps, vin, vout, M, (size_t)M * p->batch, p->batch, 0, 1, st);
   }
-#endif
-  // stage the pre-processed spectrum Z' (M complex per transform) in plan-owned memory
+  // n == 2 (M == 1, no butterfly pass): the pre-process kernel alone, staged in plan-owned memory
   {
     int rc = ensure_aux(p, (size_t)M * p->batch * es);
     if (rc) return rc;
@@ -652,21 +650,16 @@ int genfft_cuda_exec_c2r_dev(genfft_cuda_plan_t plan, void* out, const void* in,
     GENFFT_LAUNCH((c2r_pre_kernel<double>), grid, 256, 0, st, cp);
   g_launches++;
   CU_TRY(cudaGetLastError());
-  if (p->seq.passes.empty()) {  // M == 1: the inverse transform is the identity
-    CopyParams c2;
-    memset(&c2, 0, sizeof c2);
-    c2.in = p->aux;
-    c2.out = out;
-    c2.rows = p->batch;
-    c2.cols = 1;
-    c2.in_stride = 1;
-    c2.out_stride = p->out_dist / 2;
-    return launch_copy(p->precision, c2, 1, st);
-  }
-  std::vector<Step> steps;
-  seq_steps(p->seq, false, steps, false, false);
-  View vin{p->aux, M}, vout{out, p->out_dist / 2};
-  return run_chain(p, steps, vin, vout, M, (size_t)M * p->batch, p->batch, 0, 1, st);
+  // M == 1: the inverse transform is the identity
+  CopyParams c2;
+  memset(&c2, 0, sizeof c2);
+  c2.in = p->aux;
+  c2.out = out;
+  c2.rows = p->batch;
+  c2.cols = 1;
+  c2.in_stride = 1;
+  c2.out_stride = p->out_dist / 2;
+  return launch_copy(p->precision, c2, 1, st);
 }
 
 int genfft_cuda_exec_r2c_dev(genfft_cuda_plan_t plan, void* out, const void* in, void* stream) {

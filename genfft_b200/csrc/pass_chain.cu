@@ -129,7 +129,6 @@ int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, 
     const bool peers_out = fs && fs->peers && s == n - 1;
     PassParams p = st.col ? emit_col(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev)
                           : emit_1d(*st.ps, st.N, src, io[s].src.pitch, peers_out ? io[s].dst.ptr : dst, io[s].dst.pitch, gn, inverse, st.brev);
-#ifdef GENFFT_FUSED_C2R
     if (st.c2r) {
       p.in_real = 3;
       p.c2r_m = (uint32_t)st.N;
@@ -139,7 +138,6 @@ int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, 
       p.c2r_shift = plan->dit_shift;
       p.mode = M_GEN;
     }
-#endif
     if (st.real_in) {
       p.in_real = in2 ? 2 : 1;
       p.in2 = in2 ? (const char*)in2 + (size_t)off(io[s].src) * src_es : nullptr;
@@ -263,65 +261,6 @@ int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, 
     return *rc_out == GENFFT_CUDA_OK;
   };
 
-  // Chain of the FIRST two passes of a three-pass transform N = R1*R2*R3 (knob GENFFT_CUDA_CHAIN12, off by default:
-  // written without a GPU at hand, bit-identical to the unchained passes on the emulator, waiting for its measurement).
-  // It serves the sequences whose last two passes cannot be chained -- the fused-split last pass of a large real
-  // transform (C4), whose groups would be whole 16 MiB transforms.  Pass 1 writes y[j*R1 + k] for column j < R2*R3;
-  // pass 2's block a < R3 reads y[(a + i*R3)*R1 + p], i < R2: it depends on pass 1's columns j = a + i*R3.  A group is
-  // CA adjacent blocks a: pass 1's R2 tiles of columns [a0, a0 + CA) + i*R3 and pass 2's CA*(R1/CB) tiles of those
-  // blocks -- R1*R2*CA points (C4: 2 MiB).
-  auto try_chain_first_two = [&](size_t sa, size_t sb, long long units, int* rc_out) -> bool {
-    *rc_out = GENFFT_CUDA_OK;
-    const Step &A = steps[sa], &B = steps[sb];
-    if (A.col || A.brev || A.real_in || A.c2r || B.brev || B.real_in || B.c2r) return false;
-    if (io[sb].dst.ptr == io[sa].src.ptr || io[sb].dst.ptr == io[sb].src.ptr) return false;
-    const KernelEntry *ka = A.ps->k, *kb = B.ps->k;
-    if (ka->threads != kb->threads) return false;
-    const long long R1 = A.ps->R, R2 = B.ps->R, N = A.N;
-    if (A.ps->Ns != 1 || B.ps->Ns != R1 || N % (R1 * R2)) return false;
-    const long long R3 = N / (R1 * R2);
-    const long long CA = ka->C, CB = kb->C;
-    if (R3 < CA || R3 % CA || R1 % CB) return false;
-    if (R1 * R2 * CA * (long long)es > chain_max) return false;
-    ChainParams cp;
-    memset(&cp, 0, sizeof cp);
-    int rc = make_params(sa, 0, 1, &cp.a);
-    if (!rc) rc = make_params(sb, 0, 1, &cp.b);
-    if (rc) { *rc_out = rc; return false; }
-    if (cp.a.mode != M_FIRST || cp.b.mode != M_COLTW) return false;
-    // A within a group: tile i < R2 is the column block a0 + i*R3 (t1 = i), one block of CA columns (t2 = 0)
-    cp.a.n1 = (uint32_t)R2;
-    cp.a.n2 = 1;
-    cp.a.ntiles = (uint32_t)R2;
-    cp.a.ncols = (int)CA;
-    cp.a.in_t1 = R3;        // columns are adjacent input elements
-    cp.a.out_t1 = R3 * R1;  // column j's bins start at y[j*R1]
-    // B within a group: t1 = a - a0 < CA, t2 = the column blocks of p < R1 (the pass's own enumeration)
-    cp.b.n1 = (uint32_t)CA;
-    cp.b.ntiles = cp.b.n1 * cp.b.n2;
-    cp.gdiv = (uint32_t)(R3 / CA);  // groups per transform
-    cp.a_in_hi = io[sa].src.pitch; cp.a_out_hi = io[sa].dst.pitch;
-    cp.b_in_hi = io[sb].src.pitch; cp.b_out_hi = io[sb].dst.pitch;
-    cp.a_in_lo = CA;
-    cp.a_out_lo = CA * R1;
-    cp.b_in_lo = CA * cp.b.in_t1;    // in_t1 = Ns = R1 per block a
-    cp.b_out_lo = CA * cp.b.out_t1;  // out_t1 = R1*R2
-    cp.a_p_lo = cp.b_p_lo = 0;
-    cp.ngroups = (uint32_t)(units * cp.gdiv);
-    const ChainEntry* ce = find_chain(plan->precision, ka, cp.a.mode, kb, cp.b.mode, inverse ? 1 : 0);
-    if (!ce) return false;
-    if (!strides_fit_32(cp.a) || !strides_fit_32(cp.b)) return false;
-    set_tile_divisors(cp.a);
-    set_tile_divisors(cp.b);
-    cp.ta = cp.a.ntiles;
-    cp.tb = cp.b.ntiles;
-    if (!cp.ta || !cp.tb || !cp.ngroups) return false;
-    cp.lag = (uint32_t)std::max(0, env_int("GENFFT_CUDA_CHAIN_LAG", 0));
-    *rc_out = launch_chain(plan, ce, cp, stream);
-    return *rc_out == GENFFT_CUDA_OK;
-  };
-  const bool chain12_on = chain_on && env_int("GENFFT_CUDA_CHAIN12", 0) != 0;
-
   // ---- execute.  Consecutive passes along the same dimension form a segment.  The last two passes of a segment run
   // as one L2-resident chain when a chain kernel exists for their shapes.  (The older experiment GENFFT_CUDA_L2_GROUP_MB
   // ran a segment group by group with one launch per pass and group; it LOST -- C5 10.7 -> 13.4 ms at 64 MiB groups --
@@ -337,22 +276,6 @@ int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, 
     size_t run_end = seg_end;  // passes [seg_begin, run_end) are launched one by one
     bool chained = false;
     int crc = GENFFT_CUDA_OK;
-    if (seg_end - seg_begin == 3 && chain12_on && l2_group_bytes == 0 && !col &&
-        steps[seg_end - 1].N * (long long)es > chain_max &&
-        (((df || fs) && seg_end == n) || env_int("GENFFT_CUDA_CHAIN12", 0) >= 2)) {  // 2: also instead of the class-wise chain of passes 2+3
-      // the last two passes cannot be chained (their groups would be whole transforms beyond the L2 budget): chain
-      // the first two instead and stream the last one
-      chained = try_chain_first_two(seg_begin, seg_begin + 1, units, &crc);
-      if (crc) return crc;
-      if (chained) {
-        PassParams p;
-        int rc = make_params(seg_end - 1, 0, units, &p);
-        if (!rc) rc = launch_pass(plan, *steps[seg_end - 1].ps, p, stream);
-        if (rc) return rc;
-        seg_begin = seg_end;
-        continue;
-      }
-    }
     if (seg_end - seg_begin >= 2 && chain_on && l2_group_bytes == 0) {
       // passes before the pair first, over all units
       for (size_t s = seg_begin; s + 2 < seg_end; s++) {

@@ -21,7 +21,6 @@ struct PassSpec {
   const void* tw_lo = nullptr;
   int tw_shift = 0;
   const void* tw_b = nullptr;   // W_{P*Ns}^(p*i) laid out [i][p]
-  const void* tw_d = nullptr;   // whole table W_{Ns*R}^(p*k) laid out [k][p] when Ns*R is small (read instead of the three above)
 };
 
 // decomposition of one length-N transform

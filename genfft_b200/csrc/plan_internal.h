@@ -82,7 +82,7 @@ struct Step {
   bool safe;     // reads and writes the same positions per tile -> may run in place
   bool brev;
   bool real_in;
-  bool c2r = false;  // GENFFT_FUSED_C2R: the first pass builds the packed spectrum from the n/2+1 input bins while loading
+  bool c2r = false;  // half-spectrum inverse: the first pass builds the packed spectrum from the n/2+1 input bins while loading
 };
 
 // Optional override of the last pass's store: the output bin index is split at 2^part_log2 and the high

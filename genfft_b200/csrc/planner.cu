@@ -322,9 +322,7 @@ int stage_twiddle_table(int device, int precision, const KernelEntry* k, const v
   return GENFFT_CUDA_OK;
 }
 
-// inter-pass factor W_{P*Ns}^(p*i) laid out [i][p] (see PassParams::tw_b); with -DGENFFT_TWB_TILED tile-major
-// [p / C][i][p % C] for the C-column tiles of the kernel that reads it: a thread's P-1 entries are then immediate
-// offsets i*C from one address, and the rows a warp reads are adjacent cache lines
+// inter-pass factor W_{P*Ns}^(p*i) laid out [i][p] (see PassParams::tw_b): lanes read consecutive p
 static std::map<std::tuple<int, int, int, long long, int>, void*> g_pass_tables;
 
 int pass_stage_table(int device, int precision, int P, long long Ns, int C, const void** out) {
@@ -345,11 +343,7 @@ int pass_stage_table(int device, int precision, int P, long long Ns, int C, cons
     for (long long q = 0; q < Ns; q++) {
       long double c, sn;
       unit_root(((unsigned long long)q * (unsigned long long)i) % M, M, &c, &sn);
-#ifdef GENFFT_TWB_TILED
-      const size_t e = (size_t)(q / C) * (size_t)P * (size_t)C + (size_t)i * (size_t)C + (size_t)(q % C);
-#else
       const size_t e = (size_t)i * (size_t)Ns + (size_t)q;
-#endif
       if (precision == GENFFT_CUDA_F32) {
         float* t = reinterpret_cast<float*>(host.data()) + 2 * e;
         t[0] = (float)c;
@@ -364,43 +358,6 @@ int pass_stage_table(int device, int precision, int P, long long Ns, int C, cons
   CU_TRY(cudaMalloc(&d, host.size()));
   CU_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
   g_pass_tables[key] = d;
-  *out = d;
-  return GENFFT_CUDA_OK;
-}
-
-// whole inter-pass table of a pass with Ns * L = M small enough to stay in L2: entry [k][p] = W_M^(p*k), k < L, p < Ns
-static std::map<std::tuple<int, int, long long, long long>, void*> g_direct_tables;
-
-int direct_pass_table(int device, int precision, long long Ns, long long L, const void** out) {
-  std::lock_guard<std::mutex> lk(g_tw_mu);
-  auto key = std::make_tuple(device, precision, Ns, L);
-  auto it = g_direct_tables.find(key);
-  if (it != g_direct_tables.end()) {
-    *out = it->second;
-    return GENFFT_CUDA_OK;
-  }
-  const size_t es = elem_size(precision);
-  const unsigned long long M = (unsigned long long)Ns * (unsigned long long)L;
-  std::vector<unsigned char> host(es * (size_t)M);
-  for (long long k = 0; k < L; k++)
-    for (long long q = 0; q < Ns; q++) {
-      long double c, sn;
-      unit_root(((unsigned long long)q * (unsigned long long)k) % M, M, &c, &sn);
-      const size_t e = (size_t)k * (size_t)Ns + (size_t)q;
-      if (precision == GENFFT_CUDA_F32) {
-        float* t = reinterpret_cast<float*>(host.data()) + 2 * e;
-        t[0] = (float)c;
-        t[1] = (float)-sn;
-      } else {
-        double* t = reinterpret_cast<double*>(host.data()) + 2 * e;
-        t[0] = (double)c;
-        t[1] = (double)-sn;
-      }
-    }
-  void* d = nullptr;
-  CU_TRY(cudaMalloc(&d, host.size()));
-  CU_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
-  g_direct_tables[key] = d;
   *out = d;
   return GENFFT_CUDA_OK;
 }
@@ -464,11 +421,6 @@ int build_seq(Seq* seq, int device, int precision, long long N, bool wide) {
       // W_{P*Ns}^(p*i), i < P, p < Ns
       rc = pass_stage_table(device, precision, ps.k->P, Ns, ps.k->C, &ps.tw_b);
       if (rc) return rc;
-      // small M: the whole table W_M^(p*k) is read directly (2 MiB at 2^18 single precision: L2-resident)
-      if (ilog2(Ns * ps.R) <= env_int("GENFFT_CUDA_DIRECT_TW_LOG2", 18)) {
-        rc = direct_pass_table(device, precision, Ns, ps.R, &ps.tw_d);
-        if (rc) return rc;
-      }
     }
     seq->passes.push_back(ps);
     Ns *= ps.R;
@@ -495,7 +447,6 @@ static PassParams base_params(const PassSpec& ps, const void* in, void* out, int
   p.tw_shift = ps.tw_shift;
   p.tw_b = ps.tw_b;
   p.tw_b_stride = ps.Ns;
-  p.tw_d = ps.tw_d;
   return p;
 }
 

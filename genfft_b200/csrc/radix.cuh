@@ -38,21 +38,22 @@ template <typename T> __device__ __forceinline__ cpx<T> mul_mi(cpx<T> a) { retur
 // multiply by +i
 template <typename T> __device__ __forceinline__ cpx<T> mul_pi(cpx<T> a) { return cpx<T>(-a.y, a.x); }
 
-// elementwise operations on the pair (x, y); one FMUL2 / FFMA2 each for T = float in the packed variant below
+// elementwise operations on the pair (x, y); one FMUL2 / FFMA2 each for T = float (overloads below)
 template <typename T> __device__ __forceinline__ cpx<T> pair_mul(cpx<T> a, cpx<T> b) { return cpx<T>(a.x * b.x, a.y * b.y); }
 template <typename T> __device__ __forceinline__ cpx<T> pair_fma(cpx<T> a, cpx<T> b, cpx<T> c) {
   return cpx<T>(a.x * b.x + c.x, a.y * b.y + c.y);
 }
 
-// ---- packed single precision (compile-time variant GENFFT_PACKED_F32, off by default) ---------------------------------
+// ---- packed single precision ------------------------------------------------------------------------------------------
 // sm_100 has two-wide FP32 instructions on register pairs (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2).
-// An interleaved complex value IS such a pair, so a complex add is one instruction instead of two.  The multi-pass
-// kernels are bound by instruction issue (~800 warp-instructions per tile, two thirds of them
-// FP32 arithmetic, more than half of that FADD), which is what this variant attacks: the radix-16 butterfly with its
-// twiddles goes from 216 FP instructions to ~150 including the pair shuffles.  Non-template overloads: they win
-// overload resolution against the generic templates above for T = float.  Built as a separate library for A/B
-// measurement (tools/variant_bench.py); the emulator build always uses the scalar forms.
-#if defined(GENFFT_PACKED_F32) && !defined(GENFFT_EMU)
+// An interleaved complex value IS such a pair, so a complex add is one instruction instead of two, and more than half
+// of a radix-16 butterfly's arithmetic is adds (the radix-4 steps are adds only): 864 -> 744 instructions in the
+// twiddled 256-point column pass, 864 -> 688 in the 4096-point kernel, bit-identical results.  Measured on a B200
+// (profiles/r02_ab_packed_f32.log): C5 10.03 -> 9.47 ms, C2 6.19 -> 6.28 TB/s, 2^21 x 256 3.85 -> 3.74 ms.  The
+// two-instruction packed complex MULTIPLY (pair shuffles, spills under the 64-register cap) measured slower and is not
+// here.  Non-template overloads: they win overload resolution against the generic templates above for T = float; the
+// kernel-logic emulator of the CPU tests keeps the scalar forms.
+#if !defined(GENFFT_EMU)
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   unsigned long long r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -83,17 +84,6 @@ __device__ __forceinline__ cpx<float> pair_fma(cpx<float> a, cpx<float> b, cpx<f
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)), "l"(pack2(c.x, c.y)));
   return unpack2(r);
 }
-#if GENFFT_PACKED_F32 >= 2
-// (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = (a.x, a.x) * (b.x, b.y) + (-a.y, a.y) * (b.y, b.x): two instructions plus the
-// pair shuffles, against four scalar ones -- level 2 of the variant, because the shuffles cost registers (spills under
-// the 64-register cap of the twiddled column passes) and issue slots of their own
-__device__ __forceinline__ cpx<float> cmul(cpx<float> a, cpx<float> b) {
-  unsigned long long t, r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pack2(-a.y, a.y)), "l"(pack2(b.y, b.x)));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a.x, a.x)), "l"(pack2(b.x, b.y)), "l"(t));
-  return unpack2(r);
-}
-#endif
 #endif
 
 template <typename T> struct consts {

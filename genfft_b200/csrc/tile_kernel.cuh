@@ -57,17 +57,12 @@ struct PassParams {
   long long g_t1, g_c, g_i, brev_stride;
   // inter-pass Stockham twiddle W_M^(p*idx), M = Ns*L, p = t1*p_t1 + col*p_c, idx = u + i*TN, factored as
   //   W_M^(p*u)            one per thread, two-level table:  tw_hi[e >> tw_shift] * tw_lo[e & mask], e = p*u
-  //   W_M^(p*i*TN)         = W_{P*Ns}^(p*i), table tw_b[i*tw_b_stride + p] (lanes read consecutive p: coalesced); with
-  //                          GENFFT_TWB_TILED tile-major [p / C][i][p % C] (a thread's entries at immediate offsets i*C)
+  //   W_M^(p*i*TN)         = W_{P*Ns}^(p*i), table tw_b[i*tw_b_stride + p] (lanes read consecutive p: coalesced)
   const void* tw_hi;
   const void* tw_lo;
   int tw_shift;
   const void* tw_b;
   long long tw_b_stride;  // = Ns
-  // ... or, when M is small enough for the whole table to stay in L2 (planner.cu: GENFFT_CUDA_DIRECT_TW_LOG2), read
-  // directly: tw_d[k*Ns + p] = W_M^(p*k), k < L, p < Ns -- one load and one multiply per point instead of the
-  // factored form's two multiplies, and one rounding instead of three.  Lanes read consecutive p (coalesced).
-  const void* tw_d;
   // fused real-FFT split (M_ROWDIT): the tile's L-point complex transforms are the packed halves of 2L-point
   // real signals; dit_tw[k] = W_{2L}^k, k < L; dit_half: write L+1 bins only, else all 2L
   const void* dit_tw;
@@ -80,9 +75,8 @@ struct PassParams {
   // on-chip stage twiddles, one block per radix stage s >= 1 laid out [q][p]:
   //   tw_L[stage_tw_offset(s) + q*NS + p] = W_{NS*R}^(p*q)   (lanes read consecutive p: coalesced)
   const void* tw_L;
-#ifdef GENFFT_FUSED_C2R
-  // variant (waiting for its A/B): the half-spectrum inverse's pre-process (aux_kernels.cuh c2r_pre_kernel) fused into
-  // the first pass's load, in_real == 3.  Element s of the packed spectrum is built from the bins X[s] and X[M - s] of
+  // The half-spectrum inverse's pre-process (aux_kernels.cuh c2r_pre_kernel) fused into the first pass's load,
+  // in_real == 3 (measured: batched n = 4096 0.879 -> 0.743 ms, profiles/r02_ab_fused_c2r.log).  Element s of the packed spectrum is built from the bins X[s] and X[M - s] of
   // the n/2+1 input bins: s = col*c2r_sc + idx*in_stride_i relative to the transform's first bin, which is at
   // t.in_off (+ col*in_stride_c when the columns are whole transforms, c2r_sc == 0)
   uint32_t c2r_m;
@@ -90,7 +84,6 @@ struct PassParams {
   const void* c2r_hi;  // two-level table of W_n^e, n = 2M
   const void* c2r_lo;
   int c2r_shift;
-#endif
 };
 
 __host__ __device__ constexpr int stage_radix(int L, int P, int s) {
@@ -358,16 +351,6 @@ struct TileKernel {
   static __device__ __forceinline__ void apply_pass_twiddle(const PassParams& prm, const Tile& t, uint32_t col, int u,
                                                             cpx<T> (&x)[P]) {
     const uint32_t p = (t.p_base + col * (uint32_t)prm.p_c) & prm.p_mask;
-    if (prm.tw_d) {  // uniform branch: the whole launch takes the same side
-      const uint32_t ns32 = (uint32_t)prm.tw_b_stride;
-      const V* td = reinterpret_cast<const V*>(prm.tw_d) + ((size_t)(uint32_t)u * ns32 + p);
-      V w[P];
-#pragma unroll
-      for (int i = 0; i < P; i++) w[i] = ldg_strided(td, ns32, (uint32_t)(i * TN));
-#pragma unroll
-      for (int i = 0; i < P; i++) x[i] = cmul(x[i], cpx<T>(w[i].x, w[i].y));
-      return;
-    }
     const V* hi = reinterpret_cast<const V*>(prm.tw_hi);
     const V* lo = reinterpret_cast<const V*>(prm.tw_lo);
     const uint32_t e = p * (uint32_t)u;
@@ -375,18 +358,10 @@ struct TileKernel {
     V al = __ldg(lo + (e & ((1u << prm.tw_shift) - 1u)));
     const cpx<T> a = cmul(cpx<T>(ah.x, ah.y), cpx<T>(al.x, al.y));  // W_M^(p*u)
     V b[P];
-#ifdef GENFFT_TWB_TILED
-    // variant: tile-major table [p / C][i][p % C], the P-1 loads are immediate offsets from one address
-    // (-4.6 % instructions in this pass, waiting for its A/B: tools/build_variants.sh)
-    const V* tb = reinterpret_cast<const V*>(prm.tw_b) + ((p / (uint32_t)C) * (uint32_t)(P * C) + (p % (uint32_t)C));
-#pragma unroll
-    for (int i = 1; i < P; i++) b[i] = __ldg(tb + i * C);
-#else
     const V* tb = reinterpret_cast<const V*>(prm.tw_b) + p;
     const uint32_t ts32 = (uint32_t)prm.tw_b_stride;
 #pragma unroll
     for (int i = 1; i < P; i++) b[i] = ldg_strided(tb, ts32, (uint32_t)i);
-#endif
     x[0] = cmul(x[0], a);
 #pragma unroll
     for (int i = 1; i < P; i++) x[i] = cmul(x[i], cmul(a, cpx<T>(b[i].x, b[i].y)));
@@ -438,7 +413,6 @@ struct TileKernel {
       if (valid) {
         if (prm.in_real == 2) {
           x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], reinterpret_cast<const T*>(prm.in2)[off]);
-#ifdef GENFFT_FUSED_C2R
         } else if (prm.in_real == 3) {
           // Z'[s] = (X[s] + conj X[M-s]) + i (X[s] - conj X[M-s]) conj(W_n^s)   (c2r_pre_kernel, aux_kernels.cuh)
           const uint32_t sidx = col * (uint32_t)prm.c2r_sc + (uint32_t)idx * (uint32_t)prm.in_stride_i;
@@ -452,7 +426,6 @@ struct TileKernel {
           const cpx<T> w = cmul(cpx<T>(wh.x, wh.y), cpx<T>(wl.x, wl.y));  // W_n^s
           const T tx = dx * w.x + dy * w.y, ty = dy * w.x - dx * w.y;    // d * conj(w)
           x[i] = cpx<T>(ax - ty, ay + tx);
-#endif
         } else if (prm.in_real) {
           x[i] = cpx<T>(reinterpret_cast<const T*>(prm.in)[off], T(0));
         } else {
@@ -467,7 +440,7 @@ struct TileKernel {
 #pragma unroll
       for (int i = 0; i < P; i++) x[i].y = -x[i].y;
     }
-    if (prm.tw_hi || prm.tw_d) apply_pass_twiddle(prm, t, col, u, x);
+    if (prm.tw_hi) apply_pass_twiddle(prm, t, col, u, x);
     }
   }
 
@@ -628,9 +601,8 @@ struct TileKernel {
   // The split of one bin: X[q] = E - t O, E = (z + conj zp)/2, O = (z - conj zp)/2, t = i w, with the partner bin
   // zp = Z[M - q] and w = W_n^q (adjust_DIT_impl, include/genFFT/generic/fft_dit_impl_generic.inl:47-54).
   static __device__ __forceinline__ V split_bin(const cpx<T>& z, const V& zp, const cpx<T>& w) {
-#ifdef GENFFT_PACKED_F32
-    // the same value from pair operations (FFMA2 / FMUL2 in float): S = 2E, D = 2O, Q = (Im, Re) of w D,
-    // X = (S + (Q.x, -Q.y)) / 2 -- 8 instructions instead of 16
+    // written with pair operations (FFMA2 / FMUL2 on the interleaved value in float, radix.cuh): S = 2E, D = 2O,
+    // Q = (Im, Re) of w D, X = (S + (Q.x, -Q.y)) / 2 -- 8 instructions instead of the 16 of the scalar form
     const cpx<T> zq(zp.x, zp.y);
     const cpx<T> S = pair_fma(zq, cpx<T>(T(1), T(-1)), z);
     const cpx<T> D = pair_fma(zq, cpx<T>(T(-1), T(1)), z);
@@ -640,15 +612,6 @@ struct TileKernel {
     f.x = X.x;
     f.y = X.y;
     return f;
-#else
-    const T er = (z.x + zp.x) * T(0.5), ei = (z.y - zp.y) * T(0.5);
-    const T orr = (z.x - zp.x) * T(0.5), oi = (z.y + zp.y) * T(0.5);
-    const T tr = -w.y, ti = w.x;
-    V f;
-    f.x = er - (tr * orr - ti * oi);
-    f.y = ei - (tr * oi + ti * orr);
-    return f;
-#endif
   }
 
   // ---- fused real-FFT split (adjust_DIT_impl, include/genFFT/generic/fft_dit_impl_generic.inl:27-61) ----

@@ -77,23 +77,6 @@ def test_cpp_layers_on_the_emulator(binary):
     assert "PASSED" in r.stdout
 
 
-def test_pending_variants_on_the_emulator():
-    """The compile-time variants that wait for their A/B measurement (tools/build_variants.sh): GENFFT_PACKED_F32
-    (csrc/radix.cuh: FADD2 / FFMA2 on register pairs; it rewrites the real-FFT split in terms of pair operations) and
-    GENFFT_TWB_TILED (tile-major inter-pass twiddle table, host and device side).  Their index arithmetic and formulas
-    are checked here, the pair operations in their scalar form; the PTX spelling itself only a GPU can check
-    (tools/round_start.sh runs the GPU tests against the variant library)."""
-    env = dict(os.environ, GENFFT_TEST_BACKEND="emu", GENFFT_EMU_VARIANT="packed:-DGENFFT_PACKED_F32=1 -DGENFFT_TWB_TILED=1 -DGENFFT_FUSED_C2R=1")
-    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-n", str(min(8, os.cpu_count() or 1)), "-p", "no:cacheprovider",
-           "-k", "real_fft_vs_reference or r2c_c2r_random or half_spectrum_inverse", os.path.join(ROOT, "tests", "test_gpu_real_vert_2d.py"),
-           os.path.join(ROOT, "tests", "test_gpu_random_sweep.py")]
-    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
-    tail = r.stdout[-4000:] + r.stderr[-2000:]
-    assert r.returncode == 0, tail
-    m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 20, tail
-
-
 def test_abi_fuzz_on_the_emulator():
     """A short seeded run of tools/emu_fuzz.py: random sizes / batches / distances / strides / in-place calls through
     every public class on host and "device" pointers, against numpy, with sentinels around the outputs and guard pages

@@ -165,39 +165,3 @@ def test_vert_chain_is_bit_identical(cols):
     with chain(True):
         plan.transform(y1, x, cols)
     assert torch.equal(y0, y1)
-
-
-# Paths written without a GPU at hand (checked on the kernel-logic emulator only) are off by default and their GPU tests
-# opt-in: a scheduling bug in a chain would trap and take the CUDA context -- and every later test -- with it.
-# tools/round_start.sh runs them in a process of their own (GENFFT_TEST_EXPERIMENTAL=1).
-EXPERIMENTAL = os.environ.get("GENFFT_TEST_BACKEND") == "emu" or os.environ.get("GENFFT_TEST_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental path: GENFFT_TEST_EXPERIMENTAL=1 (own process)")
-@pytest.mark.parametrize("lg,batch,half,env", [
-    (19, 3, True, dict(GENFFT_CUDA_MAXLEN_F32=64, GENFFT_CUDA_CHAIN_MAX_KB=1024)),   # 64^3 packed points, small on purpose
-    (19, 2, False, dict(GENFFT_CUDA_MAXLEN_F32=64, GENFFT_CUDA_CHAIN_MAX_KB=1024)),
-    (22, 2, True, {}),                                                              # C4's shape: 128^3
-])
-def test_r2c_chain_of_the_first_two_passes(lg, batch, half, env):
-    """GENFFT_CUDA_CHAIN12=1: when the last two passes of a three-pass real transform cannot be chained (the fused-split
-    pass pairs bins across the whole transform), the first two run as one chain whose groups are pass 2's blocks a and
-    pass 1's columns a + i*R3 (pass_chain.cu: try_chain_first_two).  Same bits as the passes one by one, one launch less."""
-    if lg >= 22 and os.environ.get("GENFFT_TEST_BACKEND") == "emu":
-        pytest.skip("too large for the emulator's time budget")
-    n = 1 << lg
-    gen = torch.Generator(device="cuda").manual_seed(lg)
-    x = torch.rand((batch, n), generator=gen, device="cuda") * 2 - 1
-    nout = n // 2 + 1 if half else n
-    y0 = torch.zeros((batch, nout), dtype=torch.complex64, device="cuda")
-    y1 = torch.zeros_like(y0)
-    with chain(True, GENFFT_CUDA_CHAIN12=0, **env):
-        plan = g.RealFFT(n, np.float32, half=half, batch=batch)
-        l0 = run_counted(lambda: plan.forward(y0, x))
-    with chain(True, GENFFT_CUDA_CHAIN12=1, **env):
-        plan = g.RealFFT(n, np.float32, half=half, batch=batch)
-        l1 = run_counted(lambda: plan.forward(y1, x))
-    assert torch.equal(y0, y1), plan.describe()
-    assert (l0, l1) == (3, 2), (l0, l1, plan.describe())
-    want = np.fft.fft(x.cpu().numpy().astype(np.float64), axis=1)[:, :nout]
-    assert oracle.rel_l2(y1.cpu().numpy(), want) <= oracle.tolerance(n, np.float32)

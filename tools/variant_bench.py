@@ -15,7 +15,7 @@ for name in libs:
     _lib._lib = None
     _lib.LIB_PATH = os.path.join(ROOT, "genfft_b200", name, "libgenfft_cuda.so")
     if not os.path.exists(_lib.LIB_PATH):
-        print(f"== {name}: not built (tools/build_variants.sh)", flush=True)
+        print(f"== {name}: not built (GENFFT_LIB_OUT=genfft_b200/<dir> GENFFT_NVCC_EXTRA=... bash genfft_b200/csrc/build.sh)", flush=True)
         continue
     print(f"== {name}", flush=True)
     if "c3" in which:

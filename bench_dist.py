@@ -70,6 +70,7 @@ def main():
     ap.add_argument("--transports", type=str, default="nccl,p2p")
     ap.add_argument("--phases", action="store_true", help="p2p: also report mean ms per phase (extra untimed pass)")
     ap.add_argument("--barriers", type=str, default="flags", help="p2p transport: flags (peer memory) and/or collective")
+    ap.add_argument("--outputs", type=str, default="transposed,natural", help="which output orders to time")
     ap.add_argument("--one-d", type=int, default=0, help="instead of C5: one 1D transform of 2^ONE_D points (DistFFT1D)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -87,8 +88,9 @@ def main():
     flop = 5.0 * w * h * math.log2(w * h)
     sent = (w * h * 8 / world) * (world - 1) / world
     variants = []
+    orders = [o == "transposed" for o in args.outputs.split(",")]
     for transport in args.transports.split(","):
-        for transposed in (True, False):
+        for transposed in orders:
             if transport == "nccl":
                 variants.append((transport, transposed, 1, 1.0, 1.0, "collective"))
             else:
@@ -131,6 +133,7 @@ def main():
                     "workload": f"C5: 2D C2C fp32 {w}x{h}, slab-decomposed over {world} GPUs", "transport": transport,
                     "chunks": chunks, "frac_local": fl, "frac_remote": frm, "barrier": bar,
                     "chain": os.environ.get("GENFFT_CUDA_CHAIN", "1"),
+                    "knobs": {k: v for k, v in os.environ.items() if k.startswith("GENFFT_CUDA_")},
                     "output": "transposed (1 global transpose)" if transposed else "natural order (2 global transposes)",
                     "phases_ms_rank0_and_max": phases, "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
                     "alltoall_bytes_sent_per_gpu_per_transpose": sent,

@@ -707,7 +707,9 @@ int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaStream_t
   cp.lag = std::min(cp.lag, cp.ngroups);
   cp.ctr = static_cast<uint32_t*>(ctr);
   CU_TRY(cudaMemsetAsync(ctr, 0, need * sizeof(uint32_t), stream));
-  ce->launch(cp, (unsigned)std::min(total, resident), stream);
+  // GENFFT_CUDA_CHAIN_GRID_PCT: experiment knob, share of the resident-CTA capacity the persistent chain grid uses
+  const unsigned long long cap = std::max<unsigned long long>(1, resident * (unsigned)std::min(100, std::max(1, env_int("GENFFT_CUDA_CHAIN_GRID_PCT", 100))) / 100);
+  ce->launch(cp, (unsigned)std::min(total, cap), stream);
   g_launches++;
   g_mode_launches[ce->ma & 15]++;
   g_mode_launches[ce->mb & 15]++;

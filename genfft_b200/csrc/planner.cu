@@ -703,6 +703,11 @@ int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaStream_t
     const unsigned long long per = cp.ta + cp.tb;
     cp.lag = (uint32_t)std::min<unsigned long long>(8, 1 + (3 * resident / 2 + per - 1) / per);
     cp.lag = std::max(cp.lag, 2u);
+    // B stores to the peers (distributed transforms): its tiles are NVLink-bound and hold their CTAs several times
+    // longer than A's, so A needs more slack to stay ahead -- otherwise B tiles spin on their group counter instead of
+    // feeding the link.  Measured on 2 B200s (profiles/r02_c5_dist_2gpu_knob_sweep*.jsonl): lag 5 (the formula) 6.96 ms,
+    // 6 6.37, 8 6.26, 12 6.27, 16 6.29, 24 6.34 for C5 in natural order; 8 groups of ~4 MiB stay L2-resident.
+    if (cp.b.use_peers) cp.lag = std::max(cp.lag, 8u);
   }
   cp.lag = std::min(cp.lag, cp.ngroups);
   cp.ctr = static_cast<uint32_t*>(ctr);

@@ -45,9 +45,19 @@ def bench_one_d(args, rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             ntr = 2 if transposed else 3
+            phases = None
+            if args.phases and transport == "p2p":
+                plan.start_phase_timing()
+                for _ in range(args.steps):
+                    plan.transform(shard)
+                ph = plan.phase_times_ms()
+                pmax = torch.tensor(list(ph.values()), device="cuda", dtype=torch.float64)
+                dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+                phases = {k: round(float(v), 4) for k, v in zip(ph, pmax.tolist())}
             if rank == 0:
                 print(json.dumps({
                     "workload": f"1D C2C fp32 n=2^{args.one_d} ({h} x {w} four-step), slab-decomposed over {world} GPUs",
+                    "phases_ms_max_over_ranks": phases,
                     "transport": transport, "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
                     "output": f"transposed Z[kr][kc] = X[kr + {h} kc] (2 global transposes)" if transposed
                               else "natural order (3 global transposes)",

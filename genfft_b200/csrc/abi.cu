@@ -763,7 +763,12 @@ int genfft_cuda_plan_dist_rows(genfft_cuda_plan_t* plan, int precision, int64_t 
   p->height = rows;
   p->n = width;
   p->nparts = nparts;
-  rc = build_seq(&p->seq, p->device, precision, width, false);
+  // Rows that would fit on chip in one pass are still split in two when they are sent to peers: the one-pass kernels
+  // of 4096+ points are one or two big CTAs per SM whose loads and NVLink stores do not overlap, while a two-pass chain
+  // runs the HBM-bound pass and the link-bound storing pass (compile-time peer mode) side by side
+  // (GENFFT_CUDA_DIST_ROWS_SINGLE: longest row still done in one pass).
+  rc = build_seq(&p->seq, p->device, precision, width, false,
+                 nparts > 1 ? std::max(2, env_int("GENFFT_CUDA_DIST_ROWS_SINGLE", 16384)) : 0);
   if (rc) {
     delete p;
     return rc;

@@ -49,7 +49,9 @@ int kernel_occupancy(const KernelEntry* k, const void* func, size_t smem, int de
 
 int twiddle_table(int device, int precision, long long M, long long step, long long count, const void** out);
 int two_level_table(int device, int precision, long long M, const void** hi, const void** lo, int* shift);
-int build_seq(Seq* seq, int device, int precision, long long N, bool wide);
+// max_single > 0 overrides the longest transform done in one pass (the distributed row plans split earlier so that the
+// HBM-bound first pass and the NVLink-bound storing pass run as one chain)
+int build_seq(Seq* seq, int device, int precision, long long N, bool wide, long long max_single = 0);
 
 PassParams emit_1d(const PassSpec& ps, long long N, const void* in, long long in_dist, void* out, long long out_dist,
                    long long batch, int inverse, bool brev);

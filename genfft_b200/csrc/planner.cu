@@ -386,13 +386,13 @@ static long long max_pass_len(int precision) {
                  512);  // small tiles + one more pass beat 1-CTA-per-SM tiles once grids are one-shot (tools/sweep.sh)
 }
 
-int build_seq(Seq* seq, int device, int precision, long long N, bool wide) {
+int build_seq(Seq* seq, int device, int precision, long long N, bool wide, long long max_single) {
   seq->N = N;
   seq->wide = wide;
   seq->passes.clear();
   if (N == 1) return GENFFT_CUDA_OK;
   std::vector<long long> lens;
-  if (N <= max_single_len(precision, wide)) {
+  if (N <= (max_single > 0 ? max_single : max_single_len(precision, wide))) {
     lens.push_back(N);
   } else {
     const int lg = ilog2(N);

@@ -481,19 +481,50 @@ class DistFFT1D:
             dist.all_to_all_single(self.block.view(self.world, self.hl, self.wp), self.send, group=self.group)
             e.transpose(self.out, self.block)
             return self.out.view(-1)
+        mark = self._mark
+        mark()
         self._stream_barrier()  # peers are done with the block / slab buffers of the previous call
+        mark()
         e.cols_blocks_to_peers(x, self.block_buf.ptrs, self.rank)                    # transpose 1
+        mark()
         self._stream_barrier()
+        mark()
         e.cols_to_peers(self.block_buf.local, self.slab_buf.ptrs, self.rank, inv)    # column transforms + transpose 2
+        mark()
         self._stream_barrier()
+        mark()
         e.twiddle(self.slab, row0, inv)
+        mark()
         if self.transposed_out:
             e.rows(self.out, self.slab, inv)
+            mark()
             return self.out
         e.rows_to_peers(self.slab, self.block_buf.ptrs, self.rank, inv)              # row transforms + transpose 3
+        mark()
         self._stream_barrier()
+        mark()
         e.transpose(self.out, self.block)
+        mark()
         return self.out.view(-1)
+
+    # optional per-phase timing of the p2p path (bench_dist.py --one-d N --phases)
+    phase_names = ("barrier0", "transpose1", "barrier1", "cols+transpose2", "barrier2", "twiddle", "rows+transpose3",
+                   "barrier3", "local_transpose")
+    _events = None
+    start_phase_timing = DistFFT2D.start_phase_timing
+    _mark = DistFFT2D._mark
+
+    def phase_times_ms(self):
+        torch.cuda.synchronize()
+        ev, self._events = self._events, None
+        per = 8 if self.transposed_out else 10
+        names = self.phase_names[:6] + ("rows",) if self.transposed_out else self.phase_names
+        n = len(ev) // per
+        out = [0.0] * (per - 1)
+        for k in range(n):
+            for j in range(per - 1):
+                out[j] += ev[k * per + j].elapsed_time(ev[k * per + j + 1]) / n
+        return dict(zip(names, out))
 
     def close(self):
         if self.transport == "p2p":

@@ -332,7 +332,12 @@ class DistFFT2D:
         # p2p: stores go straight into the peers' buffers
         mark = self._mark
         mark()
-        self._stream_barrier()  # peers finished reading their block / final buffers of the previous call
+        # Peers must have finished reading their block buffers of the previous call before this call's row pass stores
+        # into them.  In natural order the previous call ended with a barrier that every rank reached AFTER its column
+        # pass (the only reader of its block buffer), so that barrier already orders it; with transposed output the
+        # call ends right after the column pass and the entry barrier is needed.
+        if self.transposed_out:
+            self._stream_barrier()
         mark()
         e.rows_to_peers(in_slab, self.block_buf.ptrs, self.rank, inv)
         mark()

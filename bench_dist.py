@@ -58,6 +58,7 @@ def bench_one_d(args, rank, world):
                 print(json.dumps({
                     "workload": f"1D C2C fp32 n=2^{args.one_d} ({h} x {w} four-step), slab-decomposed over {world} GPUs",
                     "phases_ms_max_over_ranks": phases,
+                    "knobs": {k: v for k, v in os.environ.items() if k.startswith("GENFFT_CUDA_")},
                     "transport": transport, "n_gpus": world, "ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
                     "output": f"transposed Z[kr][kc] = X[kr + {h} kc] (2 global transposes)" if transposed
                               else "natural order (3 global transposes)",

@@ -80,6 +80,8 @@ _SIGNATURES = {
     "genfft_cuda_exec_dist_rows_dev": (C.c_int, [_vp, _vp, C.POINTER(_vp), _i64, _i64, _vp, _i64, C.c_int, _vp]),
     "genfft_cuda_plan_dist_cols": (C.c_int, [_plan_p, C.c_int, _i64, _i64, C.c_int]),
     "genfft_cuda_exec_dist_cols_dev": (C.c_int, [_vp, _vp, C.POINTER(_vp), _i64, _i64, _vp, _i64, C.c_int, _vp]),
+    "genfft_cuda_exec_dist_cols_tw_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64, _i64, _vp, _i64, C.c_int, _i64, C.POINTER(C.c_int), _vp]),
+    "genfft_cuda_scatter_cols_dev": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, _i64, _vp, _i64, _i64, _i64, _vp]),
     "genfft_cuda_copy2d_dev": (C.c_int, [C.c_int, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "genfft_cuda_twiddle2d_dev": (C.c_int, [C.c_int, _vp, _i64, _i64, _i64, _i64, _i64, C.c_int, _vp]),
     "genfft_cuda_transpose_dev": (C.c_int, [C.c_int, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),

@@ -820,8 +820,61 @@ int genfft_cuda_plan_dist_cols(genfft_cuda_plan_t* plan, int precision, int64_t 
   return GENFFT_CUDA_OK;
 }
 
+static int exec_dist_cols(genfft_cuda_plan_t plan, void* out, void* const* out_peers, int64_t out_stride, int64_t col0,
+                          void* data, int64_t stride, int inverse, int64_t tw_n, int* fused, void* stream);
+
 int genfft_cuda_exec_dist_cols_dev(genfft_cuda_plan_t plan, void* out, void* const* out_peers, int64_t out_stride,
                                    int64_t col0, void* data, int64_t stride, int inverse, void* stream) {
+  return exec_dist_cols(plan, out, out_peers, out_stride, col0, data, stride, inverse, 0, nullptr, stream);
+}
+
+// The column transforms of the distributed four-step 1D transform with the twiddle W_n^(kr*c) that follows them fused
+// into the peer-storing pass.  *fused = 1 when the stores carried it, 0 when the caller still has to run
+// genfft_cuda_twiddle2d_dev on the receiving slab (shapes the compile-time peer modes do not cover).
+int genfft_cuda_exec_dist_cols_tw_dev(genfft_cuda_plan_t plan, void* const* out_peers, int64_t out_stride, int64_t col0,
+                                      void* data, int64_t stride, int inverse, int64_t n_total, int* fused, void* stream) {
+  if (!out_peers || !fused) return fail(GENFFT_CUDA_ERR_ARG, "null argument");
+  if (!is_pow2(n_total)) return fail(GENFFT_CUDA_ERR_SIZE, "n_total must be a power of two");
+  return exec_dist_cols(plan, nullptr, out_peers, out_stride, col0, data, stride, inverse, n_total, fused, stream);
+}
+
+// rows x width slab -> the peers' (H x width/nparts) column blocks at rows [row0, row0 + rows): the first global
+// transpose of the distributed four-step 1D transform in one launch (16-byte accesses)
+int genfft_cuda_scatter_cols_dev(int precision, void* const* peers, int nparts, int64_t row0, const void* in,
+                                 int64_t in_stride, int64_t rows, int64_t width, void* stream) {
+  if (precision != GENFFT_CUDA_F32 && precision != GENFFT_CUDA_F64) return fail(GENFFT_CUDA_ERR_ARG, "bad precision");
+  if (!peers || !in) return fail(GENFFT_CUDA_ERR_ARG, "null buffer");
+  if (!is_pow2(nparts) || nparts > kMaxPeers || !is_pow2(width) || width < 2 * nparts || rows < 0 || row0 < 0 ||
+      in_stride < width)
+    return fail(GENFFT_CUDA_ERR_ARG, "bad scatter arguments");
+  if (precision == GENFFT_CUDA_F32 && (((uintptr_t)in & 15) || (in_stride & 1)))
+    return fail(GENFFT_CUDA_ERR_ARG, "scatter needs 16-byte aligned rows");
+  if (!rows) return GENFFT_CUDA_OK;
+  ScatterParams sp;
+  memset(&sp, 0, sizeof sp);
+  sp.in = in;
+  for (int g = 0; g < nparts; g++) {
+    if (!peers[g] || ((uintptr_t)peers[g] & 15)) return fail(GENFFT_CUDA_ERR_ARG, "null or misaligned peer block");
+    sp.peer[g] = peers[g];
+  }
+  sp.in_stride = in_stride;
+  sp.rows = rows;
+  sp.width = width;
+  sp.row0 = row0;
+  sp.wp_log2 = ilog2(width / nparts);
+  const long long vecs = rows * (width / (precision == GENFFT_CUDA_F32 ? 2 : 1));
+  const unsigned grid = (unsigned)std::min<long long>((vecs + 255) / 256, 148LL * 64);
+  if (precision == GENFFT_CUDA_F32)
+    GENFFT_LAUNCH((scatter_cols_kernel<float>), grid, 256, 0, (cudaStream_t)stream, sp);
+  else
+    GENFFT_LAUNCH((scatter_cols_kernel<double>), grid, 256, 0, (cudaStream_t)stream, sp);
+  g_launches++;
+  CU_TRY(cudaGetLastError());
+  return GENFFT_CUDA_OK;
+}
+
+static int exec_dist_cols(genfft_cuda_plan_t plan, void* out, void* const* out_peers, int64_t out_stride, int64_t col0,
+                          void* data, int64_t stride, int inverse, int64_t tw_n, int* fused, void* stream) {
   Plan* p = plan;
   if (!p || p->kind != PLAN_DIST_COLS) return fail(GENFFT_CUDA_ERR_ARG, "not a dist_cols plan");
   if (int rc_dev = enter_exec(p)) return rc_dev;
@@ -839,8 +892,14 @@ int genfft_cuda_exec_dist_cols_dev(genfft_cuda_plan_t plan, void* out, void* con
   fs.peers = out_peers;
   fs.npeers = p->nparts;
   fs.peer_offset = col0;
+  bool did = false;
+  fs.tw_n = tw_n;
+  fs.tw_col0 = col0;
+  fs.fused = &did;
   View vout{kPeerSentinel, out_stride};
-  return run_chain(p, steps, vin, vout, p->width, elems, 0, p->width, inverse, (cudaStream_t)stream, &fs);
+  int rc = run_chain(p, steps, vin, vout, p->width, elems, 0, p->width, inverse, (cudaStream_t)stream, &fs);
+  if (fused) *fused = did ? 1 : 0;
+  return rc;
 }
 
 // out[b*out_dist + r*out_stride + c] = in[b*in_dist + r*in_stride + c], complex elements (unpack after ncclRecv)

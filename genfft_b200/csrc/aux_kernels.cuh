@@ -225,6 +225,35 @@ __global__ void __launch_bounds__(256) copy_kernel(const __grid_constant__ CopyP
   }
 }
 
+// First global transpose of the distributed four-step 1D transform as ONE launch: the (rows x width) slab of this rank
+// goes, column block by column block, into the peers' (H x width/P) blocks at rows [row0, row0 + rows):
+//   peer[c / wp][(row0 + r) * wp + c % wp] = in[r * in_stride + c],   wp = width / nparts (a power of two).
+// 16-byte accesses (two float2 or one double2 per thread), both sides coalesced; NVLink stores for the remote blocks.
+struct ScatterParams {
+  const void* in;
+  void* peer[8];
+  long long in_stride;
+  long long rows, width, row0;
+  int wp_log2;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_cols_kernel(const __grid_constant__ ScatterParams p) {
+  constexpr int EPV = sizeof(T) == 4 ? 2 : 1;  // complex elements per 16-byte vector
+  const long long vec_per_row = p.width / EPV;
+  const long long total = p.rows * vec_per_row;
+  const long long wp = 1LL << p.wp_log2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / vec_per_row;
+    const long long c = (idx - r * vec_per_row) * EPV;
+    const int g = (int)(c >> p.wp_log2);
+    const long long x = c & (wp - 1);
+    const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(p.in) + (size_t)(r * p.in_stride + c) * (2 * sizeof(T)));
+    *reinterpret_cast<float4*>(reinterpret_cast<char*>(p.peer[g]) + (size_t)((p.row0 + r) * wp + x) * (2 * sizeof(T))) = v;
+  }
+}
+
 // Inter-step twiddle of the distributed four-step 1D transform (N = H*W points seen as an H x W row-major matrix whose
 // row slabs live on different GPUs): after the length-H column transforms, element (kr, c) is multiplied by
 // W_N^(kr*c) before the length-W row transforms.  In place on a (rows x cols) slab whose first row is global row row0.

@@ -168,8 +168,15 @@ int run_chain(Plan* plan, const std::vector<Step>& steps_in, View in, View out, 
         // which the compile-time peer modes resolve per register (tile_kernel.cuh, M_PEER*)
         const int pm = fs->npeers == 2 ? M_PEER2 : fs->npeers == 4 ? M_PEER4 : fs->npeers == 8 ? M_PEER8 : -1;
         if (pm >= 0 && twiddled_mode == M_COLTW && !st.brev && !st.real_in && st.ps->k->launch[pm][inverse ? 1 : 0] &&
-            (1LL << sh) * fs->npeers == st.ps->R && env_int("GENFFT_CUDA_PEER_MODES", 1))
+            (1LL << sh) * fs->npeers == st.ps->R && env_int("GENFFT_CUDA_PEER_MODES", 1)) {
           p.mode = pm;
+          if (fs->tw_n >= 8 && fs->tw_n <= (1LL << 31) && st.col && env_int("GENFFT_CUDA_FUSED_1D_TWIDDLE", 1)) {
+            int rc = two_level_table(plan->device, plan->precision, fs->tw_n, &p.tw2_hi, &p.tw2_lo, &p.tw2_shift);
+            if (rc) return rc;
+            p.tw2_col0 = (uint32_t)(fs->tw_col0 + g0);
+            if (fs->fused) *fs->fused = true;
+          }
+        }
       } else {
         p.out_stride_khi = fs->part_stride;
       }

@@ -95,6 +95,10 @@ struct FinalStore {
   int npeers = 0;
   long long part_stride = 0;
   long long peer_offset = 0;  // elements added to every peer pointer
+  // distributed four-step 1D: multiply by W_{tw_n}^(row * (tw_col0 + column)) in the storing pass (compile-time peer
+  // modes only); *fused reports whether it was done, otherwise the caller runs the twiddle pass itself
+  long long tw_n = 0, tw_col0 = 0;
+  bool* fused = nullptr;
 };
 
 // Optional fusion of the real-FFT split into the last pass of a multi-pass chain (M_COLTWDIT).

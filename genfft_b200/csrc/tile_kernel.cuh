@@ -63,6 +63,13 @@ struct PassParams {
   int tw_shift;
   const void* tw_b;
   long long tw_b_stride;  // = Ns
+  // M_PEER* only, distributed four-step 1D transform: the twiddle W_n^(kr*c) between its column and row transforms
+  // fused into the column pass's peer store (kr = output row p + k*Ns, c = tw2_col0 + column), two-level table
+  // tw2_hi[e >> tw2_shift] * tw2_lo[e & mask] of W_n; null = no twiddle
+  const void* tw2_hi;
+  const void* tw2_lo;
+  int tw2_shift;
+  uint32_t tw2_col0;
   // fused real-FFT split (M_ROWDIT): the tile's L-point complex transforms are the packed halves of 2L-point
   // real signals; dit_tw[k] = W_{2L}^k, k < L; dit_half: write L+1 bins only, else all 2L
   const void* dit_tw;
@@ -301,10 +308,12 @@ struct TileKernel {
     uint32_t p_base;
     uint32_t col0;
     long long g_base;
+    uint32_t grp_col;  // chains: first column of the tile's group within the pass (column passes; 0 otherwise)
   };
 
   static __device__ __forceinline__ Tile decode(const PassParams& prm, uint32_t tile) {
     Tile t;
+    t.grp_col = 0;
     if constexpr (ROWLIKE) {  // columns are whole transforms; no outer tile indices
       t.col0 = tile * C;
       t.in_off = t.out_off = 0;
@@ -454,6 +463,22 @@ struct TileKernel {
       constexpr int G = P / (NPEER ? NPEER : 1);  // consecutive register slots that go to the same rank
       const uint32_t s32 = (uint32_t)prm.out_stride_k;
       const long long off = base + (long long)u * prm.out_stride_k;
+      if (prm.tw2_hi) {  // uniform: the four-step 1D transform's W_n^(kr*c), kr = p + k*Ns, c = global column
+        const V* hi = reinterpret_cast<const V*>(prm.tw2_hi);
+        const V* lo = reinterpret_cast<const V*>(prm.tw2_lo);
+        const uint32_t ns = (uint32_t)prm.tw_b_stride;
+        const uint32_t cg = prm.tw2_col0 + t.grp_col + col;
+        const uint32_t kr0 = ((t.p_base & prm.p_mask) + (uint32_t)u * ns) * cg;
+        const uint32_t step = (uint32_t)TN * ns * cg;
+        const uint32_t mask = (1u << prm.tw2_shift) - 1u;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+          const uint32_t e = kr0 + (uint32_t)i * step;  // < n <= 2^31
+          const V wh = __ldg(hi + (e >> prm.tw2_shift));
+          const V wl = __ldg(lo + (e & mask));
+          x[i] = cmul(x[i], cmul(cpx<T>(wh.x, wh.y), cpx<T>(wl.x, wl.y)));
+        }
+      }
 #pragma unroll
       for (int g = 0; g < NPEER; g++) {
         V* dst = reinterpret_cast<V*>(prm.out_peer[g]) + off;
@@ -773,6 +798,7 @@ struct TileKernel {
     t.in_off += in_g;
     t.out_off += out_g;
     t.p_base += p_g;
+    if constexpr (PEER) t.grp_col = (uint32_t)out_g;  // column passes: the group offset is a column count
     load<LDOP>(prm, t, c_ld, u_ld, x);
     int c = c_ld, u = u_ld;
     run_stages<0>(prm, x, smem, c, u, c_st, u_st);

@@ -147,12 +147,20 @@ class CudaSlabEngine:
                                                        self._stream()))
         self._fan_out(launch)
 
-    def cols_to_peers(self, block_ptr: int, peer_ptrs, rank: int, inv: bool):
+    def cols_to_peers(self, block_ptr: int, peer_ptrs, rank: int, inv: bool, twiddle_n: int = 0) -> bool:
+        """Column transforms of this rank's (H x W/P) block, the rows scattered to the peers' row slabs.  With
+        ``twiddle_n`` (distributed four-step 1D) the factor W_n^(kr*c) is fused into those stores; returns whether it
+        was (False: the caller applies ``twiddle`` on the receiving slab)."""
         arr = (C.c_void_p * self.p)(*peer_ptrs)
         if self.chunks == 1:
+            if twiddle_n:
+                fused = C.c_int(0)
+                check(lib().genfft_cuda_exec_dist_cols_tw_dev(self._cols, arr, self.w, rank * self.wp, block_ptr, self.wp,
+                                                              int(inv), twiddle_n, C.byref(fused), self._stream()))
+                return bool(fused.value)
             check(lib().genfft_cuda_exec_dist_cols_dev(self._cols, None, arr, self.w, rank * self.wp, block_ptr,
                                                        self.wp, int(inv), self._stream()))
-            return
+            return False
         ck = self.wp // self.chunks
 
         def launch(k, plans):
@@ -160,6 +168,7 @@ class CudaSlabEngine:
                                                        block_ptr + k * ck * self.esize, self.wp, int(inv),
                                                        self._stream()))
         self._fan_out(launch)
+        return False
 
     def cols_ptr(self, out, block_ptr: int, inv: bool):
         check(lib().genfft_cuda_exec_dist_cols_dev(self._cols, out.data_ptr(), None, self.wp, 0, block_ptr, self.wp,
@@ -173,7 +182,13 @@ class CudaSlabEngine:
                                            self.w, self.wp, self.hl, self.wp, self.p, self._stream()))
 
     def cols_blocks_to_peers(self, slab, peer_ptrs, rank: int):
-        """The same blocks stored straight into the peers' (H x W/P) block buffers at rows [rank*H/P, ...)."""
+        """slab[r, g*Wp:(g+1)*Wp] stored straight into peer g's (H x W/P) block buffer at rows [rank*H/P, ...): the first
+        global transpose of the four-step 1D transform, one launch with 16-byte accesses."""
+        arr = (C.c_void_p * self.p)(*peer_ptrs)
+        if slab.data_ptr() % 16 == 0 and all(q % 16 == 0 for q in peer_ptrs) and self.wp >= 2:
+            check(lib().genfft_cuda_scatter_cols_dev(self.precision, arr, self.p, rank * self.hl, slab.data_ptr(), self.w,
+                                                     self.hl, self.w, self._stream()))
+            return
         for g in range(self.p):
             check(lib().genfft_cuda_copy2d_dev(self.precision, peer_ptrs[g] + rank * self.hl * self.wp * self.esize,
                                                self.wp, 0, slab.data_ptr() + g * self.wp * self.esize, self.w, 0,
@@ -494,11 +509,13 @@ class DistFFT1D:
         mark()
         self._stream_barrier()
         mark()
-        e.cols_to_peers(self.block_buf.local, self.slab_buf.ptrs, self.rank, inv)    # column transforms + transpose 2
+        # column transforms + transpose 2, the twiddle W_n^(kr*c) fused into the peer stores when the pass allows it
+        fused = e.cols_to_peers(self.block_buf.local, self.slab_buf.ptrs, self.rank, inv, twiddle_n=self.n)
         mark()
         self._stream_barrier()
         mark()
-        e.twiddle(self.slab, row0, inv)
+        if not fused:
+            e.twiddle(self.slab, row0, inv)
         mark()
         if self.transposed_out:
             e.rows(self.out, self.slab, inv)

@@ -201,6 +201,13 @@ int genfft_cuda_copy2d_dev(int precision, void* out, int64_t out_stride, int64_t
  * reference corresponds to it (genFFT is single-threaded, one address space).
  * twiddle2d: data[r*stride + c] *= W_N^((row0 + r) * c) in place (conjugated for the inverse), N = n_total.
  * transpose: out[c*out_stride + r] = in[r*in_stride + c] (natural-order output of the four-step transform). */
+/* dist_cols with the four-step twiddle W_n^(kr*c) fused into the peer stores (*fused = 1), or not (*fused = 0: the
+ * caller runs twiddle2d on the receiving slab).  scatter_cols: the first global transpose (row slab -> the peers' column
+ * blocks at rows [row0, row0 + rows)) in one launch. */
+int genfft_cuda_exec_dist_cols_tw_dev(genfft_cuda_plan_t plan, void* const* out_peers, int64_t out_stride, int64_t col0,
+                                      void* data, int64_t stride, int inverse, int64_t n_total, int* fused, void* stream);
+int genfft_cuda_scatter_cols_dev(int precision, void* const* peers, int nparts, int64_t row0, const void* in,
+                                 int64_t in_stride, int64_t rows, int64_t width, void* stream);
 int genfft_cuda_twiddle2d_dev(int precision, void* data, int64_t stride, int64_t rows, int64_t cols, int64_t row0,
                               int64_t n_total, int inverse, void* stream);
 int genfft_cuda_transpose_dev(int precision, void* out, int64_t out_stride, const void* in, int64_t in_stride,

@@ -35,6 +35,7 @@
 
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) double2 { double x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;

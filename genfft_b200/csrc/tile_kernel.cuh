@@ -464,19 +464,31 @@ struct TileKernel {
       const uint32_t s32 = (uint32_t)prm.out_stride_k;
       const long long off = base + (long long)u * prm.out_stride_k;
       if (prm.tw2_hi) {  // uniform: the four-step 1D transform's W_n^(kr*c), kr = p + k*Ns, c = global column
+        // k = u + i*TN: W^(kr*c) = a * s^i with a = W^((p + u*Ns)*c) and s = W^(TN*Ns*c), two table lookups per thread;
+        // s^i = (s^4)^(i/4) * s^(i%4) from a few squarings (at most four multiplications deep, so the rounding stays
+        // at the level of the two-level table itself) instead of sixteen dependent lookups in L2
         const V* hi = reinterpret_cast<const V*>(prm.tw2_hi);
         const V* lo = reinterpret_cast<const V*>(prm.tw2_lo);
         const uint32_t ns = (uint32_t)prm.tw_b_stride;
         const uint32_t cg = prm.tw2_col0 + t.grp_col + col;
-        const uint32_t kr0 = ((t.p_base & prm.p_mask) + (uint32_t)u * ns) * cg;
-        const uint32_t step = (uint32_t)TN * ns * cg;
         const uint32_t mask = (1u << prm.tw2_shift) - 1u;
-#pragma unroll
-        for (int i = 0; i < P; i++) {
-          const uint32_t e = kr0 + (uint32_t)i * step;  // < n <= 2^31
+        auto root = [&](uint32_t e) {  // e < n <= 2^31
           const V wh = __ldg(hi + (e >> prm.tw2_shift));
           const V wl = __ldg(lo + (e & mask));
-          x[i] = cmul(x[i], cmul(cpx<T>(wh.x, wh.y), cpx<T>(wl.x, wl.y)));
+          return cmul(cpx<T>(wh.x, wh.y), cpx<T>(wl.x, wl.y));
+        };
+        const cpx<T> a = root(((t.p_base & prm.p_mask) + (uint32_t)u * ns) * cg);
+        const cpx<T> s1 = root((uint32_t)TN * ns * cg);
+        const cpx<T> s2 = cmul(s1, s1), s3 = cmul(s2, s1), s4 = cmul(s2, s2);
+        static_assert(P == 16, "the fused twiddle is written for 16 points per thread");
+        cpx<T> ah = a;  // a * s^(4*hi)
+#pragma unroll
+        for (int h4 = 0; h4 < 4; h4++) {
+          x[4 * h4 + 0] = cmul(x[4 * h4 + 0], ah);
+          x[4 * h4 + 1] = cmul(x[4 * h4 + 1], cmul(ah, s1));
+          x[4 * h4 + 2] = cmul(x[4 * h4 + 2], cmul(ah, s2));
+          x[4 * h4 + 3] = cmul(x[4 * h4 + 3], cmul(ah, s3));
+          if (h4 < 3) ah = cmul(ah, s4);
         }
       }
 #pragma unroll

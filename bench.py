@@ -185,6 +185,9 @@ def reference_arm(args, rank: int, world: int) -> int:
 # extras.C5_dist: BASELINE.json configs[4] on the N GPUs of the run (N > 1).  It runs in CHILD processes (one per rank,
 # their own process group) so that a failure or a hang there cannot take the contract line with it.
 # ---------------------------------------------------------------------------------------------------------------------
+# what an all-to-all of SM-issued peer stores with NO compute reaches on this pool's 8-GPU boxes, GB/s per direction and
+# GPU (tools/alltoall_store_bench.cu, profiles/r02_alltoall_store_ceiling.log; 8-byte stores in 256-byte runs)
+A2A_STORE_CEILING_GBS = {2: 659.0, 4: 680.0, 8: 664.0}
 C5_W = C5_H = 32768
 C5_COLS = [0, 1, 15, 16, 4097, 16384, 20011, 32767]  # sampled output columns: both halves, tile edges, odd places
 
@@ -280,6 +283,10 @@ def c5_dist_child(args) -> int:
         r = {"ms": ms, "gflops": flop / (ms * 1e-3) / 1e9, "global_transposes": ntr,
              "nvlink_floor_ms_at_900GBs": floor900, "frac_of_nvlink_900": floor900 / ms,
              "frac_of_nvlink_770_measured_peer_copy": (ntr * sent / 770e9 * 1e3) / ms,
+             "frac_of_measured_alltoall_store_ceiling": (ntr * sent / (A2A_STORE_CEILING_GBS[world] * 1e9) * 1e3) / ms
+             if world in A2A_STORE_CEILING_GBS else None,
+             "alltoall_store_ceiling_source": "constant from profiles/r02_alltoall_store_ceiling.log (a store-only "
+                                              "all-to-all kernel, no FFT); NOT measured by this run",
              "phases_ms_max_over_ranks": {k: round(v, 4) for k, v in zip(ph, pmax)}}
         return plan, res, r
 

@@ -47,16 +47,16 @@ __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
 }
 #endif
 
-template <typename T, int THREADS>
+template <typename T, int THREADS, int P = 16>
 constexpr int chain_min_blocks() {
-  return min_blocks<T, THREADS>();
+  return min_blocks<T, THREADS, P>();
 }
 
 // KA, KB: TileKernel instantiations with the same thread count.  The grid is persistent (one CTA per resident slot);
 // every CTA loops over tickets and fetches the next one while it works on the current tile, so the atomic's round
 // trip is off the critical path.
 template <typename T, class KA, class KB>
-__global__ void __launch_bounds__(KA::THREADS, chain_min_blocks<T, KA::THREADS>())
+__global__ void __launch_bounds__(KA::THREADS, chain_min_blocks<T, KA::THREADS, KA::TN == 0 ? 16 : KA::P_PER_THREAD>())
 fft_chain_kernel(const __grid_constant__ ChainParams cp) {
   static_assert(KA::THREADS == KB::THREADS, "chained passes must have the same CTA size");
   GENFFT_DYN_SMEM(smem_raw);

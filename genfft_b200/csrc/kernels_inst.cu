@@ -57,6 +57,7 @@ void register_kernels_f64_small(std::vector<KernelEntry>& v) {
   ADD_B(double, 256, 16, 8);
   ADD_W(double, 256, 16, 16);
   ADD_W(double, 256, 8, 16);
+  ADD_W(double, 256, 8, 8);
   ADD_W(double, 128, 8, 16);
 }
 #elif GENFFT_KSET == 4

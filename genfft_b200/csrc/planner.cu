@@ -154,10 +154,10 @@ const ChainEntry* find_chain(int precision, const KernelEntry* ka, int ma, const
     register_chains_2(chains);
     register_chains_3(chains);
   });
-  if (ka->P != 16 || kb->P != 16) return nullptr;
+  if (ka->P != kb->P) return nullptr;
   const int prec = precision == GENFFT_CUDA_F32 ? 0 : 1;
   for (auto& e : chains)
-    if (e.precision == prec && e.la == ka->L && e.ca == ka->C && e.ma == ma && e.lb == kb->L && e.cb == kb->C &&
+    if (e.precision == prec && e.p == ka->P && e.la == ka->L && e.ca == ka->C && e.ma == ma && e.lb == kb->L && e.cb == kb->C &&
         e.mb == mb && e.inv == inv)
       return &e;
   return nullptr;

@@ -80,6 +80,7 @@ KernelEntry make_entry() {
 // ---- L2-resident pass chains (chain_kernel.cuh): pairs of wide shapes with equal CTA sizes ----
 struct ChainEntry {
   int precision;  // 0: float, 1: double (GENFFT_CUDA_F32 / F64)
+  int p;          // points per thread of both passes
   int la, ca, ma, lb, cb, mb, inv;
   int threads;
   size_t smem;
@@ -94,12 +95,13 @@ void launch_chain_t(const ChainParams& cp, unsigned grid, cudaStream_t stream) {
 }
 
 // INV applies to the compile-time-direction modes; M_GEN takes the direction from PassParams::inverse
-template <typename T, int LA, int CA, int MA, int LB, int CB, int MB, bool INV>
+template <typename T, int LA, int CA, int MA, int LB, int CB, int MB, bool INV, int PP = 16>
 void add_chain(std::vector<ChainEntry>& v) {
-  using KA = TileKernel<T, LA, 16, CA, MA, MA == M_GEN ? false : INV>;
-  using KB = TileKernel<T, LB, 16, CB, MB, MB == M_GEN ? false : INV>;
+  using KA = TileKernel<T, LA, PP, CA, MA, MA == M_GEN ? false : INV>;
+  using KB = TileKernel<T, LB, PP, CB, MB, MB == M_GEN ? false : INV>;
   ChainEntry e = {};
   e.precision = sizeof(T) == 4 ? 0 : 1;
+  e.p = PP;
   e.la = LA; e.ca = CA; e.ma = MA;
   e.lb = LB; e.cb = CB; e.mb = MB;
   e.inv = INV ? 1 : 0;
@@ -116,6 +118,15 @@ void add_peer_chains(std::vector<ChainEntry>& v) {
   add_chain<T, LA, CA, M_FIRST, LB, CB, MB, true>(v);
   add_chain<T, LA, CA, M_COL, LB, CB, MB, false>(v);
   add_chain<T, LA, CA, M_COL, LB, CB, MB, true>(v);
+}
+
+// the chains of a plain (single-GPU) 1D transform for shapes with PP points per thread
+template <typename T, int PP, int LA, int CA, int LB, int CB>
+void add_chain_shapes_1d(std::vector<ChainEntry>& v) {
+  add_chain<T, LA, CA, M_FIRST, LB, CB, M_COLTW, false, PP>(v);
+  add_chain<T, LA, CA, M_FIRST, LB, CB, M_COLTW, true, PP>(v);
+  add_chain<T, LA, CA, M_COLTW, LB, CB, M_COLTW, false, PP>(v);
+  add_chain<T, LA, CA, M_COLTW, LB, CB, M_COLTW, true, PP>(v);
 }
 
 // every mode pair the plans chain, for one pair of shapes

@@ -279,6 +279,7 @@ __device__ __forceinline__ double2 ldg_strided(const double2* base, uint32_t str
 template <typename T, int L, int P, int C, int MODE, bool INV>
 struct TileKernel {
   static constexpr int TN = L / P;
+  static constexpr int P_PER_THREAD = P;
   static constexpr int THREADS = TN * C;
   static constexpr int NST = num_stages(L, P);
   static constexpr int PADSH = pad_shift<T, P>();
@@ -366,9 +367,28 @@ struct TileKernel {
     V ah = __ldg(hi + (e >> prm.tw_shift));
     V al = __ldg(lo + (e & ((1u << prm.tw_shift) - 1u)));
     const cpx<T> a = cmul(cpx<T>(ah.x, ah.y), cpx<T>(al.x, al.y));  // W_M^(p*u)
-    V b[P];
     const V* tb = reinterpret_cast<const V*>(prm.tw_b) + p;
     const uint32_t ts32 = (uint32_t)prm.tw_b_stride;
+    if constexpr (P == 16) {
+      // b_i = W_{16 Ns}^(p*i): rows 1, 4, 8, 12 of the table are read, the rest are products b_{4h} * b_j with
+      // b_2 = b_1^2, b_3 = b_2 b_1 -- 4 loads and 33 multiplications instead of 15 loads and 32 multiplications, at
+      // most three roundings deep (measured, profiles/r02_ab_twiddle_powers.log: C3 272.7 -> 258 us, 2^21 x 256
+      // 3.79 -> 3.65 ms, C5 -1..-5 %; rel-L2 vs genFFT 2.4e-7 in float, 9e-16 in double at 2^24)
+      const V v1 = ldg_strided(tb, ts32, 1u), v4 = ldg_strided(tb, ts32, 4u), v8 = ldg_strided(tb, ts32, 8u),
+              v12 = ldg_strided(tb, ts32, 12u);
+      const cpx<T> b1(v1.x, v1.y);
+      const cpx<T> b2 = cmul(b1, b1), b3 = cmul(b2, b1);
+      const cpx<T> a4[4] = {a, cmul(a, cpx<T>(v4.x, v4.y)), cmul(a, cpx<T>(v8.x, v8.y)), cmul(a, cpx<T>(v12.x, v12.y))};
+#pragma unroll
+      for (int h = 0; h < 4; h++) {
+        x[4 * h + 0] = cmul(x[4 * h + 0], a4[h]);
+        x[4 * h + 1] = cmul(x[4 * h + 1], cmul(a4[h], b1));
+        x[4 * h + 2] = cmul(x[4 * h + 2], cmul(a4[h], b2));
+        x[4 * h + 3] = cmul(x[4 * h + 3], cmul(a4[h], b3));
+      }
+      return;
+    }
+    V b[P];
 #pragma unroll
     for (int i = 1; i < P; i++) b[i] = ldg_strided(tb, ts32, (uint32_t)i);
     x[0] = cmul(x[0], a);
@@ -912,7 +932,7 @@ struct TileKernel {
 
 // resident-thread target per SM: 1024 (64 registers) in float, 512 (128 registers) in double, where a
 // thread's 16 complex points alone are 64 registers
-template <typename T, int THREADS>
+template <typename T, int THREADS, int P = 16>
 constexpr int min_blocks() {
 #ifndef GENFFT_F64_TARGET_THREADS
 #define GENFFT_F64_TARGET_THREADS 512
@@ -920,13 +940,14 @@ constexpr int min_blocks() {
 #ifndef GENFFT_F32_TARGET_THREADS
 #define GENFFT_F32_TARGET_THREADS 1024
 #endif
-  constexpr int target = sizeof(T) == 4 ? GENFFT_F32_TARGET_THREADS : GENFFT_F64_TARGET_THREADS;
+  // 8 double-complex points per thread are 32 registers of data: those shapes can run at 64 registers, 1024 threads
+  constexpr int target = sizeof(T) == 4 ? GENFFT_F32_TARGET_THREADS : (P <= 8 ? 1024 : GENFFT_F64_TARGET_THREADS);
   return THREADS >= target ? 1 : target / THREADS;
 }
 
 template <typename T, int L, int P, int C, int MODE, bool INV>
 __global__ void __launch_bounds__(TileKernel<T, L, P, C, MODE, INV>::THREADS,
-                                  min_blocks<T, TileKernel<T, L, P, C, MODE, INV>::THREADS>())
+                                  min_blocks<T, TileKernel<T, L, P, C, MODE, INV>::THREADS, P>())
 fft_tile_kernel(const __grid_constant__ PassParams prm) {
   GENFFT_DYN_SMEM(smem_raw);
   TileKernel<T, L, P, C, MODE, INV>::body(prm, reinterpret_cast<cpx<T>*>(smem_raw));

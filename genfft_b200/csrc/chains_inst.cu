@@ -27,7 +27,6 @@ void register_chains_3(std::vector<ChainEntry>& v) {
   add_chain_shapes<double, 256, 8, 128, 16>(v);
   add_chain_shapes<double, 256, 8, 256, 8>(v);
   add_chain_shapes<double, 512, 8, 512, 8>(v);
-  add_chain_shapes_1d<double, 8, 256, 8, 256, 8>(v);  // 8 points per thread: 64 registers, twice the resident warps
 }
 #else
 #error "GENFFT_CSET must be 0..3"

@@ -56,14 +56,10 @@ void register_kernels_f64_small(std::vector<KernelEntry>& v) {
   ADD_B(double, 128, 16, 16);
   ADD_B(double, 256, 16, 8);
   ADD_W(double, 256, 16, 16);
-  ADD_W(double, 256, 8, 16);
-  ADD_W(double, 256, 8, 8);
-  ADD_W(double, 128, 8, 16);
 }
 #elif GENFFT_KSET == 4
 void register_kernels_f64_mid(std::vector<KernelEntry>& v) {
   ADD_B(double, 512, 16, 8);
-  ADD_W(double, 512, 8, 8);
   ADD_N(double, 1024, 16, 4);
   ADD_W(double, 1024, 16, 8);
   ADD_N(double, 2048, 16, 2);

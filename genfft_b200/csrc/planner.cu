@@ -166,10 +166,10 @@ const ChainEntry* find_chain(int precision, const KernelEntry* ka, int ma, const
 // Kernel shape for a length-L pass.  Narrow (contiguous batched) use takes the fewest sequences per CTA.  Wide (column)
 // use wants row segments of at least 128 bytes and CTAs of ~256 threads in float / ~128 in double (128 registers per
 // thread there): measured best with one-shot grids (tools/sweep.sh).  Tuning knobs: GENFFT_CUDA_WIDE_C_{F32,F64}
-// forces the column count, GENFFT_CUDA_P_{F32,F64} picks the points-per-thread variant where several are compiled.
+// forces the column count.
 const KernelEntry* find_kernel(int precision, long long L, bool wide) {
   const bool f32 = precision == GENFFT_CUDA_F32;
-  const int want_p = wide ? env_int(f32 ? "GENFFT_CUDA_P_F32" : "GENFFT_CUDA_P_F64", 16) : 16;
+  const int want_p = 16;  // every compiled shape holds 16 points per thread (8-point double shapes lost twice)
   const int forced = wide ? env_int(f32 ? "GENFFT_CUDA_WIDE_C_F32" : "GENFFT_CUDA_WIDE_C_F64", 0) : 0;
   const long long min_seg = f32 ? 16 : 8, target_threads = f32 ? 256 : 128;
   const long long desired = forced ? forced : std::max(min_seg, target_threads * 16 / std::max(16LL, L));

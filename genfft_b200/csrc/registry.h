@@ -120,15 +120,6 @@ void add_peer_chains(std::vector<ChainEntry>& v) {
   add_chain<T, LA, CA, M_COL, LB, CB, MB, true>(v);
 }
 
-// the chains of a plain (single-GPU) 1D transform for shapes with PP points per thread
-template <typename T, int PP, int LA, int CA, int LB, int CB>
-void add_chain_shapes_1d(std::vector<ChainEntry>& v) {
-  add_chain<T, LA, CA, M_FIRST, LB, CB, M_COLTW, false, PP>(v);
-  add_chain<T, LA, CA, M_FIRST, LB, CB, M_COLTW, true, PP>(v);
-  add_chain<T, LA, CA, M_COLTW, LB, CB, M_COLTW, false, PP>(v);
-  add_chain<T, LA, CA, M_COLTW, LB, CB, M_COLTW, true, PP>(v);
-}
-
 // every mode pair the plans chain, for one pair of shapes
 template <typename T, int LA, int CA, int LB, int CB>
 void add_chain_shapes(std::vector<ChainEntry>& v) {

@@ -940,8 +940,9 @@ constexpr int min_blocks() {
 #ifndef GENFFT_F32_TARGET_THREADS
 #define GENFFT_F32_TARGET_THREADS 1024
 #endif
-  // 8 double-complex points per thread are 32 registers of data: those shapes can run at 64 registers, 1024 threads
-  constexpr int target = sizeof(T) == 4 ? GENFFT_F32_TARGET_THREADS : (P <= 8 ? 1024 : GENFFT_F64_TARGET_THREADS);
+  // (8 double-complex points per thread at 64 registers, i.e. twice the resident warps, were measured in round 2:
+  // C3 311 us against 258 us for 16 points at 128 registers -- profiles/r02_c3_8_points_per_thread_64_registers.log)
+  constexpr int target = sizeof(T) == 4 ? GENFFT_F32_TARGET_THREADS : GENFFT_F64_TARGET_THREADS;
   return THREADS >= target ? 1 : target / THREADS;
 }
 

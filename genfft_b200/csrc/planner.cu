@@ -664,6 +664,13 @@ int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaStream_t
   {
     // one counter block per stream: two executions of the plan on different streams may run at the same time
     std::lock_guard<std::mutex> lk(plan->mu);
+    if (plan->chain_ctrs.size() >= 32 && !plan->chain_ctrs.count(stream)) {
+      // a plan that has seen many (short-lived) streams: drop the blocks of the others once the device is idle
+      CU_TRY(cudaDeviceSynchronize());
+      for (auto& kv : plan->chain_ctrs)
+        if (kv.second.ptr) cudaFree(kv.second.ptr);
+      plan->chain_ctrs.clear();
+    }
     Plan::ChainCtr& cc = plan->chain_ctrs[stream];
     if (cc.count < need) {
       if (cc.ptr) {

@@ -165,3 +165,22 @@ def test_vert_chain_is_bit_identical(cols):
     with chain(True):
         plan.transform(y1, x, cols)
     assert torch.equal(y0, y1)
+
+
+@pytest.mark.no_emu  # needs real streams
+def test_chained_plan_across_many_streams():
+    """A chained plan executed on more streams than it keeps counter blocks for (32): the blocks are recycled, results
+    stay bit-identical."""
+    n, batch = 1 << 16, 4
+    x = torch.view_as_complex(torch.rand((batch, n, 2), device="cuda") * 2 - 1)
+    plan = g.FFT(n, np.float32, batch=batch)
+    want = torch.empty_like(x)
+    plan.forward(want, x)
+    torch.cuda.synchronize()
+    for k in range(40):
+        s = torch.cuda.Stream()
+        y = torch.empty_like(x)
+        with torch.cuda.stream(s):
+            plan.forward(y, x)
+        s.synchronize()
+        assert torch.equal(y, want)

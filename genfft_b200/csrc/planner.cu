@@ -659,33 +659,6 @@ void build_fast_path(Plan* p) {
 
 // One launch for two consecutive passes with the intermediate kept in L2 (chain_kernel.cuh).
 int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaStream_t stream) {
-  const size_t need = 1 + (size_t)cp.ngroups;
-  void* ctr = nullptr;
-  {
-    // one counter block per stream: two executions of the plan on different streams may run at the same time
-    std::lock_guard<std::mutex> lk(plan->mu);
-    if (plan->chain_ctrs.size() >= 32 && !plan->chain_ctrs.count(stream)) {
-      // a plan that has seen many (short-lived) streams: drop the blocks of the others once the device is idle
-      CU_TRY(cudaDeviceSynchronize());
-      for (auto& kv : plan->chain_ctrs)
-        if (kv.second.ptr) cudaFree(kv.second.ptr);
-      plan->chain_ctrs.clear();
-    }
-    Plan::ChainCtr& cc = plan->chain_ctrs[stream];
-    if (cc.count < need) {
-      if (cc.ptr) {
-        CU_TRY(cudaStreamSynchronize(stream));  // earlier launches on this stream are the block's only users
-        CU_TRY(cudaFree(cc.ptr));
-        cc.ptr = nullptr;
-        cc.count = 0;
-      }
-      const size_t cap = std::max<size_t>(need, 4096);
-      if (cudaMalloc(&cc.ptr, cap * sizeof(uint32_t)) != cudaSuccess)
-        return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc of %zu chain counters failed", cap);
-      cc.count = cap;
-    }
-    ctr = cc.ptr;
-  }
   int occ = 0;
   {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
@@ -717,6 +690,33 @@ int launch_chain(Plan* plan, const ChainEntry* ce, ChainParams& cp, cudaStream_t
     if (cp.b.use_peers) cp.lag = std::max(cp.lag, 8u);
   }
   cp.lag = std::min(cp.lag, cp.ngroups);
+  // One counter block per stream: two executions of the plan on different streams may run at the same time.  The block
+  // is picked, zeroed and handed to the launch under the plan's lock: another thread that recycles the blocks (below)
+  // must not free one between these steps.
+  const size_t need = 1 + (size_t)cp.ngroups;
+  void* ctr = nullptr;
+  std::lock_guard<std::mutex> lk(plan->mu);
+  if (plan->chain_ctrs.size() >= 32 && !plan->chain_ctrs.count(stream)) {
+    // a plan that has seen many (short-lived) streams: drop the blocks of the others once the device is idle
+    CU_TRY(cudaDeviceSynchronize());
+    for (auto& kv : plan->chain_ctrs)
+      if (kv.second.ptr) cudaFree(kv.second.ptr);
+    plan->chain_ctrs.clear();
+  }
+  Plan::ChainCtr& cc = plan->chain_ctrs[stream];
+  if (cc.count < need) {
+    if (cc.ptr) {
+      CU_TRY(cudaStreamSynchronize(stream));  // earlier launches on this stream are the block's only users
+      CU_TRY(cudaFree(cc.ptr));
+      cc.ptr = nullptr;
+      cc.count = 0;
+    }
+    const size_t cap = std::max<size_t>(need, 4096);
+    if (cudaMalloc(&cc.ptr, cap * sizeof(uint32_t)) != cudaSuccess)
+      return fail(GENFFT_CUDA_ERR_ALLOC, "cudaMalloc of %zu chain counters failed", cap);
+    cc.count = cap;
+  }
+  ctr = cc.ptr;
   cp.ctr = static_cast<uint32_t*>(ctr);
   CU_TRY(cudaMemsetAsync(ctr, 0, need * sizeof(uint32_t), stream));
   // GENFFT_CUDA_CHAIN_GRID_PCT: experiment knob, share of the resident-CTA capacity the persistent chain grid uses

@@ -186,8 +186,9 @@ def reference_arm(args, rank: int, world: int) -> int:
 # their own process group) so that a failure or a hang there cannot take the contract line with it.
 # ---------------------------------------------------------------------------------------------------------------------
 # what an all-to-all of SM-issued peer stores with NO compute reaches on this pool's 8-GPU boxes, GB/s per direction and
-# GPU (tools/alltoall_store_bench.cu, profiles/r02_alltoall_store_ceiling.log; 8-byte stores in 256-byte runs)
-A2A_STORE_CEILING_GBS = {2: 659.0, 4: 680.0, 8: 664.0}
+# GPU (tools/alltoall_store_bench.cu, profiles/r02_alltoall_store_ceiling.log; 8-byte stores in 256-byte runs; for a
+# pair the 1 GiB figure of tools/peer_store_bench.cu, profiles/r02_peer_store_shape_bench_2gpu.log)
+A2A_STORE_CEILING_GBS = {2: 705.0, 4: 680.0, 8: 664.0}
 C5_W = C5_H = 32768
 C5_COLS = [0, 1, 15, 16, 4097, 16384, 20011, 32767]  # sampled output columns: both halves, tile edges, odd places
 

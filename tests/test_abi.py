@@ -83,6 +83,25 @@ def test_argument_errors_before_any_cuda_call(lib):
     assert lib.genfft_cuda_plan_c2c_2d(ctypes.byref(h), 0, 12, 8) == 1
     assert lib.genfft_cuda_exec_c2c(None, None, None, 0) == 2
     assert lib.genfft_cuda_plan_destroy(None) == 0
+    # round 2: distances of a batch must hold a whole transform, checked before any CUDA call
+    assert lib.genfft_cuda_plan_c2c_1d(ctypes.byref(h), 0, 256, 4, 100, 0) == 2
+    assert b"in_dist" in lib.genfft_cuda_last_error_string()
+    assert lib.genfft_cuda_plan_c2c_1d(ctypes.byref(h), 0, 256, 4, 0, -256) == 2
+    assert lib.genfft_cuda_plan_r2c_1d(ctypes.byref(h), 0, 256, 4, 1, 0, 100) == 2
+    assert lib.genfft_cuda_plan_c2r_1d(ctypes.byref(h), 0, 256, 4, 0, 128) == 2
+    assert lib.genfft_cuda_plan_c2c_1d(ctypes.byref(h), 0, 2, 1 << 40, 0, 0) == 1  # volume beyond the 32-bit tile counts
+    # the new host-side entry points validate their arguments too
+    out = ctypes.c_void_p()
+    node = ctypes.c_int()
+    assert lib.genfft_cuda_host_alloc(None, 16, 1, ctypes.byref(node)) == 2
+    assert lib.genfft_cuda_host_alloc(ctypes.byref(out), 0, 1, ctypes.byref(node)) == 2
+    assert lib.genfft_cuda_host_free(ctypes.c_void_p(4096)) == 2           # not one of its blocks
+    assert lib.genfft_cuda_separate_2x_real(7, None, None, None, 8) == 2  # bad precision
+    assert lib.genfft_cuda_separate_2x_real(0, None, None, None, 8) == 2  # null buffers
+    peers = (ctypes.c_void_p * 8)()
+    assert lib.genfft_cuda_scatter_cols_dev(0, peers, 3, 0, ctypes.c_void_p(4096), 64, 4, 64, None) == 2  # ranks not 2^k
+    assert lib.genfft_cuda_scatter_cols_dev(0, None, 2, 0, ctypes.c_void_p(4096), 64, 4, 64, None) == 2
+    assert lib.genfft_cuda_debug_mode_launch_count(99) == 0
 
 
 def test_host_mirror_semantics_without_gpu():

@@ -13,6 +13,32 @@ if "2x" in sys.argv[1:]:  # only RealFFT2D::forward_2x: first pass reading two i
     torch.cuda.synchronize()
     print("2x cases done")
     sys.exit(0)
+if "dist" in sys.argv[1:]:  # round 2: peer-store modes (chained and not), fused four-step twiddle, one-launch scatter,
+    # played by one process on one device (the peers' buffers are local allocations)
+    from genfft_b200.dist import CudaSlabEngine, four_step_shape
+    for dt, cd in ((np.float32, torch.complex64), (np.float64, torch.complex128)):
+        for world in (2, 4, 8):
+            w, h = 32768, 8
+            hl, wp = h // world, w // world
+            eng = [CudaSlabEngine(w, h, world, dt) for _ in range(world)]
+            blocks = [torch.zeros((h, wp), dtype=cd, device="cuda") for _ in range(world)]
+            for r in range(world):
+                x = torch.randn(hl, w, dtype=cd, device="cuda")
+                eng[r].rows_to_peers(x, [b.data_ptr() for b in blocks], r, bool(r & 1))
+            n = 1 << 24
+            hh, ww = four_step_shape(n, world)
+            e1 = [CudaSlabEngine(ww, hh, world, dt) for _ in range(world)]
+            blk = [torch.zeros((hh, ww // world), dtype=cd, device="cuda") for _ in range(world)]
+            mids = [torch.zeros((hh // world, ww), dtype=cd, device="cuda") for _ in range(world)]
+            for r in range(world):
+                e1[r].cols_blocks_to_peers(torch.randn(hh // world, ww, dtype=cd, device="cuda"), [b.data_ptr() for b in blk], r)
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert e1[r].cols_to_peers(blk[r].data_ptr(), [m.data_ptr() for m in mids], r, False, twiddle_n=n)
+            torch.cuda.synchronize()
+            del eng, e1, blocks, blk, mids
+    print("dist cases done")
+    sys.exit(0)
 for dt, cd in ((np.float32, torch.complex64), (np.float64, torch.complex128)):
     rd = torch.float32 if dt == np.float32 else torch.float64
     # M_ROW / M_ROWTMA (needs >= 4 tiles per SM)

@@ -620,6 +620,14 @@ int resolve_pass(const Plan* plan, const PassSpec& ps, const PassParams& p, Reso
   }
   r->launch = ps.k->launch[mode][inv];
   r->mode = mode;
+  // Programmatic dependent launch (fft_tile_kernel) for grids of at most one wave, where the launch latency is the
+  // cost: a forward + inverse pair of N = 1024 from a C loop 8.19 -> 5.15 us, N = 16384 24.6 -> 20.3 us; large grids
+  // gain nothing and C2 measured 4 % slower with it (profiles/r02_ab_programmatic_dependent_launch.log).
+  // GENFFT_CUDA_PDL: 0 never, 1 (default) single-wave grids, 2 always.
+  {
+    const int pdl = env_int("GENFFT_CUDA_PDL", 1);
+    q.pdl = pdl >= 2 || (pdl == 1 && (long long)r->grid <= (long long)plan->num_sms * occ) ? 1 : 0;
+  }
   return GENFFT_CUDA_OK;
 }
 

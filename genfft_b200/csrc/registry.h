@@ -24,6 +24,22 @@ struct KernelEntry {
 template <typename T, int L, int P, int C, int MODE, bool INV>
 void launch_tile(const PassParams& prm, int grid, cudaStream_t stream) {
   using K = TileKernel<T, L, P, C, MODE, INV>;
+#ifndef GENFFT_EMU
+  if (prm.pdl) {  // programmatic stream serialization: see fft_tile_kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)K::THREADS);
+    cfg.dynamicSmemBytes = K::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, fft_tile_kernel<T, L, P, C, MODE, INV>, prm);
+    return;
+  }
+#endif
   GENFFT_LAUNCH((fft_tile_kernel<T, L, P, C, MODE, INV>), grid, K::THREADS, K::SMEM_BYTES, stream, prm);
 }
 

@@ -43,6 +43,7 @@ struct PassParams {
   int ncols;                 // valid columns along t2*C + c (tail tiles are masked)
   int map_load, map_store;   // 0 = lanes across columns (A), 1 = lanes along the sequence (B)
   int mode;                  // host side only: which compiled addressing mode to launch (enum Mode)
+  int pdl;                   // host side only: launch with programmatic stream serialization (see fft_tile_kernel)
   float grid_frac;           // host side only: fraction of the resident-CTA capacity to launch (0 = all)
   uint32_t tiles_per_cta;    // 0: grid-stride loop over tiles (persistent grid); K > 0: CTA b owns tiles [b*K, b*K+K)
   // tile -> (t0, t1, t2) without integer division: q = umulhi(x, mul) >> shr (mul == 0: divisor is 1), see fast_div()
@@ -951,6 +952,16 @@ __global__ void __launch_bounds__(TileKernel<T, L, P, C, MODE, INV>::THREADS,
                                   min_blocks<T, TileKernel<T, L, P, C, MODE, INV>::THREADS, P>())
 fft_tile_kernel(const __grid_constant__ PassParams prm) {
   GENFFT_DYN_SMEM(smem_raw);
+#ifndef GENFFT_EMU
+  // Programmatic dependent launch: when this grid was launched with programmatic stream serialization, it may become
+  // resident while the previous kernel of the stream is still running -- launch_dependents lets the NEXT kernel do the
+  // same as soon as every CTA of this grid has started, wait blocks until the previous grid has completed and its
+  // memory is visible.  Nothing above the wait touches memory a kernel writes, so back-to-back small transforms (a
+  // forward + inverse pair of N = 1024 is two single-CTA launches) no longer pay a full launch latency each.  Both
+  // instructions are no-ops in a normally launched grid.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   TileKernel<T, L, P, C, MODE, INV>::body(prm, reinterpret_cast<cpx<T>*>(smem_raw));
 }
 

@@ -32,6 +32,12 @@ for name in libs:
     if "c2r" in which:
         q.c2r(4096, 1 << 16)
         q.c2r(1 << 22, 64)
+    if "small2" in which:  # single-pass sizes, and two batches that fit in L2 (evict-first stores must not hurt them)
+        for n in (256, 1024, 16384):
+            q.c2c(n, (1 << 28) // n)
+        q.c2c(4096, 1024)
+        q.c2c(4096, 256)
+        q.r2c(4096, 1 << 16)
     if "c2" in which:
         q.c2c(4096, 1 << 16)
     torch.cuda.empty_cache()

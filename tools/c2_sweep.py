@@ -40,3 +40,4 @@ for name in libs:
     for t in tiles:
         v = sorted(res[t])
         print(f"{name} tiles={t}: ms/launch min {v[0]:.4f} med {v[len(v)//2]:.4f} max {v[-1]:.4f}  {nbytes / v[len(v)//2] / 1e6:.0f} GB/s (med)", flush=True)
+        print(f"   in order: " + " ".join(f"{x:.4f}" for x in res[t]), flush=True)
